@@ -1,0 +1,190 @@
+/*
+ * cco_b200.h -- C ABI of the Blackwell-native Correlated Cross-Occurrence (CCO) model builder.
+ *
+ * This is the drop-in boundary for the train hot path of actionml/universal-recommender.
+ * It replaces the two calls the reference makes into Apache Mahout 0.13.0:
+ *
+ *   SimilarityAnalysis.cooccurrencesIDSs(Array[IndexedDataset], randomSeed,
+ *       maxInterestingItemsPerThing, maxNumInteractions)       src/main/scala/URAlgorithm.scala:323-329
+ *   SimilarityAnalysis.crossOccurrenceDownsampled(
+ *       List[DownsamplableCrossOccurrenceDataset], randomSeed) src/main/scala/URAlgorithm.scala:343-346
+ *
+ * A Scala object with those two signatures marshals each IndexedDataset's matrix into CSR and
+ * calls cco_train() over JNI (INTEGRATION.md has the stub); everything else in the reference
+ * (engine.json, DataSource, Preparator, URModel, EsClient) is untouched.
+ *
+ * Plain C: pointers and sizes only, no CUDA/torch types.  All functions return 0 on success or
+ * a negative cco_status_t; cco_last_error() gives the message (thread-local).  There is no CPU
+ * fallback: every entry point that computes fails with CCO_E_CUDA when no sm_100 device exists.
+ */
+#ifndef CCO_B200_H
+#define CCO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CCO_ABI_VERSION 1
+
+typedef enum {
+  CCO_OK = 0,
+  CCO_E_INVALID_ARG = -1,    /* mirrors IllegalArgumentException / Preconditions.checkArgument in Mahout */
+  CCO_E_CUDA = -2,           /* CUDA runtime / no usable device */
+  CCO_E_NCCL = -3,
+  CCO_E_OOM = -4,
+  CCO_E_SHAPE_MISMATCH = -5, /* matrices do not share the user (row) space -- Preparator.scala:47-77 */
+  CCO_E_UNSUPPORTED = -6
+} cco_status_t;
+
+/*
+ * Input: one binary user x item matrix per event type, exactly what Preparator builds as
+ * IndexedDatasetSpark (src/main/scala/Preparator.scala:160-214): every stored value is 1.0
+ * (RandomAccessSparseVector.setQuick(col, 1.0), :201-208) so there is no values array;
+ * n_rows is the size of the shared user dictionary (newRowCardinality, :213), including users
+ * with no interaction in this event type.  Column indices may come in any order inside a row
+ * and duplicates collapse (setQuick semantics).  The library never keeps host pointers.
+ */
+typedef struct {
+  int64_t n_rows;         /* U, must be equal for all matrices of one call, < 2^31 (Mahout keys are Int) */
+  int32_t n_cols;         /* I of this event type, < 2^31 - 1 */
+  const int64_t *row_ptr; /* [n_rows + 1], row_ptr[0] == 0, monotone */
+  const int32_t *col_idx; /* [row_ptr[n_rows]], each in [0, n_cols) */
+} cco_csr_t;
+
+/*
+ * Per-matrix parameters = DownsamplableCrossOccurrenceDataset(iD, maxElementsPerRow,
+ * maxInterestingElements, minLLROpt) as built at src/main/scala/URAlgorithm.scala:336-340.
+ * Defaults in the reference: 500 / 50 / None (URAlgorithm.scala:54,56,338-340).
+ */
+typedef struct {
+  int32_t max_interactions; /* m >= 1: maxItemsPerUser | maxEventsPerEventType */
+  int32_t top_k;            /* k in [1, CCO_MAX_TOP_K]: maxCorrelatorsPerItem | maxCorrelatorsPerEventType */
+  int32_t has_min_llr;      /* Option[Double].isDefined */
+  double min_llr;           /* keep a cell only if llr >= min_llr */
+} cco_indicator_params_t;
+
+#define CCO_MAX_TOP_K 2048
+
+/* cco_train flags */
+enum {
+  /* Row sample rate of sampleDownAndBinarize: 0 = real min(m,d)/d (default); 1 = literal
+   * Int/Int division recalled from Mahout 0.13.0 (1 if d <= m else 0).  DESIGN.md "Downsampling". */
+  CCO_FLAG_ROWRATE_INTDIV = 1,
+  /* LogLikelihood.entropy evaluation order: 0 = left-to-right subtraction (default);
+   * 2 = varargs form xLogX(sum) - (sum of xLogX).  Last-bit difference only. */
+  CCO_FLAG_ENTROPY_VARARGS = 2,
+  /* inputs are already canonical (columns strictly ascending inside each row): skip the check */
+  CCO_FLAG_ASSUME_CANONICAL = 4
+};
+
+/*
+ * Sampler (the repo's definition; Mahout's java.util.Random-per-Spark-block stream is not
+ * reproducible by construction).  For a stored (user u, item j) of a matrix with
+ * raw row count d_u and raw column count c_j:
+ *   mix64(z): z ^= z>>30; z *= 0xbf58476d1ce4e5b9; z ^= z>>27; z *= 0x94d049bb133111eb; z ^= z>>31
+ *   h    = mix64( mix64(((uint64)(uint32)seed << 32) | (uint32)u) + (uint64)(uint32)j * 0x9e3779b97f4a7c15 )
+ *   u01  = (double)(h >> 11) * 2^-53
+ *   keep = u01 <= min( min(m,d_u)/d_u , min(m,c_j)/c_j )          (fp64, IEEE division)
+ * Identity whenever every d_u <= m and c_j <= m -- the regime where parity with Mahout is exact.
+ */
+
+typedef struct {
+  int32_t device;     /* CUDA device ordinal for this context */
+  int32_t rank;       /* rank of this context in a multi-GPU job, 0 if world_size == 1 */
+  int32_t world_size; /* number of cooperating contexts (one process per GPU) */
+  int32_t reserved;
+  /* world_size > 1: 128-byte NCCL unique id obtained from cco_nccl_unique_id() on rank 0 and
+   * distributed by the host (any transport); ignored when world_size == 1 */
+  const unsigned char *nccl_unique_id;
+} cco_config_t;
+
+typedef struct cco_ctx cco_ctx_t;
+typedef struct cco_result cco_result_t;
+
+/* Per-call statistics (the metrics/logging hook; replaces the logger.info dimension lines of
+ * Preparator.scala:60,66,74 and feeds bench.py's roofline arithmetic). */
+typedef struct {
+  int64_t n_users;
+  int64_t nnz_in_total;         /* stored entries handed in, all matrices */
+  int64_t nnz_downsampled[16];  /* per matrix (first 16), after canonicalise + downsample */
+  int64_t products[16];         /* per indicator: P(A',B') = sum_u degA'(u) * degB'(u), this rank's rows */
+  int64_t distinct_cells[16];   /* per indicator: nnz(A'^T B') visited, this rank's rows */
+  int64_t out_nnz[16];          /* per indicator: kept cells, this rank's rows */
+  float ms_h2d, ms_prepare, ms_cooccurrence, ms_d2h, ms_total; /* CUDA-event times of this call */
+  float ms_indicator[16];       /* per indicator: row kernels only */
+  int32_t n_kernel_launches;    /* kernels of this library launched by the call */
+  int32_t n_mats;
+} cco_stats_t;
+
+int cco_abi_version(void);
+const char *cco_last_error(void);
+const char *cco_status_string(int status);
+
+/* number of sm_100 (B200) devices visible; <0 on CUDA failure */
+int cco_device_count(void);
+
+/* world_size > 1 only: fill 128 bytes on rank 0, hand them to every rank's cco_create */
+int cco_nccl_unique_id(unsigned char out[128]);
+
+int cco_create(const cco_config_t *cfg, cco_ctx_t **out);
+int cco_destroy(cco_ctx_t *ctx);
+
+/* Pinned host memory the caller can fill directly (e.g. wrapped as a direct ByteBuffer by the
+ * JNI shim) so cco_train's host->device copies run at PCIe speed.  Optional. */
+int cco_host_alloc(cco_ctx_t *ctx, size_t bytes, void **out);
+int cco_host_free(cco_ctx_t *ctx, void *p);
+
+/*
+ * The whole hot path, mats[0] = primary (A):
+ *   A' = sampleDownAndBinarize(A, seed, params[0].m); N = n_rows; colA = nnzPerColumn(A')
+ *   out[0] = top-k_0 by LLR of A'^T A' (diagonal excluded), out[i] = top-k_i by LLR of A'^T B'_i
+ * In a multi-GPU job every rank passes the same matrices; rank r computes a work-balanced range
+ * of primary-item rows and its result holds only those rows (cco_result_row_range).
+ * One call at a time per context.
+ */
+int cco_train(cco_ctx_t *ctx, int32_t n_mats, const cco_csr_t *mats, const cco_indicator_params_t *params,
+              int32_t seed, uint32_t flags, cco_result_t **out);
+
+/* SimilarityAnalysis.cooccurrencesIDSs convenience: one global (k, m) for every matrix */
+int cco_cooccurrences_idss(cco_ctx_t *ctx, int32_t n_mats, const cco_csr_t *mats, int32_t seed,
+                           int32_t max_interesting_items_per_thing, int32_t max_num_interactions,
+                           uint32_t flags, cco_result_t **out);
+
+/*
+ * Result = List[IndexedDataset]; element i has rowIDs = A.columnIDs, columnIDs = B_i.columnIDs.
+ * Indicator i as CSR over primary items: rows sorted by (llr desc, col asc), so the consumer's
+ * sortBy(-llr) in package.scala:100-108 is a no-op.  count = k11 of each kept cell.
+ * Pointers are owned by the result (pinned host memory) and live until cco_result_free.
+ * row_ptr has (row_end - row_begin + 1) entries, relative to this rank's first row.
+ */
+int cco_result_num_matrices(const cco_result_t *r);
+int cco_result_row_range(const cco_result_t *r, int32_t i, int64_t *row_begin, int64_t *row_end);
+int cco_result_matrix(const cco_result_t *r, int32_t i, int64_t *n_rows, int32_t *n_cols,
+                      const int64_t **row_ptr, const int32_t **col_idx, const double **llr,
+                      const int32_t **count);
+int cco_result_stats(const cco_result_t *r, cco_stats_t *out);
+int cco_result_free(cco_result_t *r);
+
+/*
+ * Debug/parity entry (tests only): full integer co-occurrence matrix A^T B of two canonical
+ * binary matrices computed by the same accumulation kernel as cco_train, no LLR, no top-k.
+ * Output CSR over the columns of A with ascending column ids, malloc'ed; free with cco_free.
+ */
+int cco_debug_cooccurrence(cco_ctx_t *ctx, const cco_csr_t *a, const cco_csr_t *b, int64_t **row_ptr,
+                           int32_t **col_idx, int32_t **count);
+/* Debug/parity entry (tests only): sampleDownAndBinarize of one matrix on the device. */
+int cco_debug_downsample(cco_ctx_t *ctx, const cco_csr_t *m, int32_t max_interactions, int32_t seed,
+                         uint32_t flags, int64_t **row_ptr, int32_t **col_idx, int32_t *raw_col_counts,
+                         int32_t *new_col_counts);
+/* Debug/parity entry (tests only): the device LLR of n cells. */
+int cco_debug_llr(cco_ctx_t *ctx, int64_t n, const int64_t *k11, const int64_t *k12, const int64_t *k21,
+                  const int64_t *k22, uint32_t flags, double *out);
+void cco_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CCO_B200_H */

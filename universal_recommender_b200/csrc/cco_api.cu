@@ -1,0 +1,1058 @@
+// cco_api.cu -- C ABI (include/cco_b200.h) and host orchestration of the sm_100a CCO model builder.
+//
+// Replaces Mahout's SimilarityAnalysis.cooccurrencesIDSs / crossOccurrenceDownsampled as called from
+// /root/reference/src/main/scala/URAlgorithm.scala:323-329,343-346.  No CPU fallback: every compute
+// entry fails with CCO_E_CUDA when no CUDA device is usable.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cub/cub.cuh>
+#include <mutex>
+#include <vector>
+
+#include "../../include/cco_b200.h"
+#include "cco_kernels.cuh"
+
+namespace cco {
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int set_error(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CK(expr)                                                                                      \
+  do {                                                                                                \
+    cudaError_t _e = (expr);                                                                          \
+    if (_e != cudaSuccess)                                                                            \
+      return set_error(_e == cudaErrorMemoryAllocation ? CCO_E_OOM : CCO_E_CUDA, "%s: %s (%s:%d)", #expr, \
+                       cudaGetErrorString(_e), __FILE__, __LINE__);                                   \
+  } while (0)
+#define CKR(expr)            \
+  do {                       \
+    int _r = (expr);         \
+    if (_r != CCO_OK) return _r; \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// NCCL, loaded lazily (only multi-GPU contexts need it)
+// ------------------------------------------------------------------------------------------------
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+struct Nccl {
+  void *h = nullptr;
+  int (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+};
+static Nccl g_nccl;
+static std::mutex g_nccl_mu;
+static int load_nccl() {
+  std::lock_guard<std::mutex> lk(g_nccl_mu);
+  if (g_nccl.h) return CCO_OK;
+  void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return set_error(CCO_E_NCCL, "cannot load libnccl.so.2: %s", dlerror());
+#define SYM(field, name)                                                         \
+  *(void **)(&g_nccl.field) = dlsym(h, name);                                    \
+  if (!g_nccl.field) return set_error(CCO_E_NCCL, "libnccl: missing symbol %s", name);
+  SYM(GetUniqueId, "ncclGetUniqueId")
+  SYM(CommInitRank, "ncclCommInitRank")
+  SYM(CommDestroy, "ncclCommDestroy")
+  SYM(AllReduce, "ncclAllReduce")
+  SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+  g_nccl.h = h;
+  return CCO_OK;
+}
+constexpr int kNcclInt32 = 2, kNcclSum = 0;  // ncclInt32, ncclSum (nccl.h enum values)
+
+}  // namespace cco
+
+using namespace cco;
+
+// ------------------------------------------------------------------------------------------------
+// context / result objects
+// ------------------------------------------------------------------------------------------------
+struct PinnedBuf {
+  void *p;
+  size_t cap;
+  bool used;
+};
+
+struct cco_ctx {
+  int device = 0, rank = 0, world = 1;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev[8] = {};
+  std::vector<PinnedBuf> pinned;
+  std::mutex mu;
+  ncclComm_t comm = nullptr;
+  int launches = 0;
+
+  void *pinned_get(size_t bytes) {
+    std::lock_guard<std::mutex> lk(mu);
+    if (bytes == 0) bytes = 16;
+    int best = -1;
+    for (size_t i = 0; i < pinned.size(); ++i)
+      if (!pinned[i].used && pinned[i].cap >= bytes && (best < 0 || pinned[i].cap < pinned[best].cap)) best = (int)i;
+    if (best >= 0) {
+      pinned[best].used = true;
+      return pinned[best].p;
+    }
+    void *p = nullptr;
+    size_t cap = (bytes + (1u << 20) - 1) & ~((size_t)(1u << 20) - 1);
+    if (cudaHostAlloc(&p, cap, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    pinned.push_back({p, cap, true});
+    return p;
+  }
+  void pinned_put(void *p) {
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto &b : pinned)
+      if (b.p == p) b.used = false;
+  }
+};
+
+struct ResultMat {
+  int64_t row_begin = 0, row_end = 0;
+  int32_t n_cols = 0;
+  int64_t *row_ptr = nullptr;
+  int32_t *col = nullptr;
+  double *llr = nullptr;
+  int32_t *cnt = nullptr;
+};
+struct cco_result {
+  cco_ctx *ctx = nullptr;
+  std::vector<ResultMat> mats;
+  cco_stats_t stats;
+};
+
+namespace cco {
+
+// per-call device arena on top of the stream-ordered allocator
+struct Arena {
+  cudaStream_t s;
+  std::vector<void *> ptrs;
+  explicit Arena(cudaStream_t st) : s(st) {}
+  ~Arena() {
+    for (void *p : ptrs) cudaFreeAsync(p, s);
+  }
+  template <typename T>
+  int alloc(T **out, size_t n) {
+    void *p = nullptr;
+    size_t bytes = std::max<size_t>(n * sizeof(T), 16);
+    cudaError_t e = cudaMallocAsync(&p, bytes, s);
+    if (e != cudaSuccess) return set_error(CCO_E_OOM, "cudaMallocAsync(%zu bytes): %s", bytes, cudaGetErrorString(e));
+    ptrs.push_back(p);
+    *out = (T *)p;
+    return CCO_OK;
+  }
+  void release(void *p) {
+    for (size_t i = 0; i < ptrs.size(); ++i)
+      if (ptrs[i] == p) {
+        cudaFreeAsync(p, s);
+        ptrs.erase(ptrs.begin() + i);
+        return;
+      }
+  }
+};
+
+static inline int grid_for(long long work_items, int block, int sm_count, int waves = 8) {
+  long long g = (work_items + block - 1) / block;
+  long long cap = (long long)sm_count * waves;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+struct DevRaw {  // a matrix as uploaded (int64 row_ptr like the host)
+  long long n_rows = 0;
+  int32_t n_cols = 0;
+  long long nnz = 0;
+  long long *rp = nullptr;
+  int32_t *col = nullptr;
+};
+struct DevMat {  // after canonicalise + downsample
+  long long n_rows = 0;
+  int32_t n_cols = 0;
+  uint32_t *rp = nullptr;  // [n_rows+1]
+  int32_t *col = nullptr;
+  int32_t *marg = nullptr;  // post-sample column counts
+};
+
+static int exclusive_sum_u32(cco_ctx *c, Arena &ar, const uint32_t *in, uint32_t *out, long long n) {
+  size_t tb = 0;
+  CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, in, out, n, c->stream));
+  void *tmp;
+  CKR(ar.alloc((char **)&tmp, tb));
+  CK(cub::DeviceScan::ExclusiveSum(tmp, tb, in, out, n, c->stream));
+  c->launches += 2;
+  ar.release(tmp);
+  return CCO_OK;
+}
+static int exclusive_sum_i64(cco_ctx *c, Arena &ar, const long long *in, long long *out, long long n) {
+  size_t tb = 0;
+  CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, in, out, n, c->stream));
+  void *tmp;
+  CKR(ar.alloc((char **)&tmp, tb));
+  CK(cub::DeviceScan::ExclusiveSum(tmp, tb, in, out, n, c->stream));
+  c->launches += 2;
+  ar.release(tmp);
+  return CCO_OK;
+}
+
+// canonicalisation slow path: sort (row,col) keys, drop duplicates, rebuild row_ptr
+static int canonicalize_device(cco_ctx *c, Arena &ar, DevRaw &m) {
+  if (m.nnz == 0) return CCO_OK;
+  unsigned long long *k0, *k1;
+  CKR(ar.alloc(&k0, m.nnz));
+  CKR(ar.alloc(&k1, m.nnz));
+  k_expand_keys<<<grid_for(m.n_rows * kSG, 256, c->sm_count), 256, 0, c->stream>>>(m.n_rows, m.rp, m.col, k0);
+  c->launches++;
+  int row_bits = 1;
+  while ((1LL << row_bits) < m.n_rows) ++row_bits;
+  cub::DoubleBuffer<unsigned long long> db(k0, k1);
+  size_t tb = 0;
+  CK(cub::DeviceRadixSort::SortKeys(nullptr, tb, db, m.nnz, 0, 32 + row_bits, c->stream));
+  void *tmp;
+  CKR(ar.alloc((char **)&tmp, tb));
+  CK(cub::DeviceRadixSort::SortKeys(tmp, tb, db, m.nnz, 0, 32 + row_bits, c->stream));
+  c->launches += 8;
+  ar.release(tmp);
+  unsigned long long *sorted = db.Current(), *other = db.Alternate();
+  uint32_t *flag, *pos;
+  CKR(ar.alloc(&flag, m.nnz + 1));
+  CKR(ar.alloc(&pos, m.nnz + 1));
+  CK(cudaMemsetAsync(flag + m.nnz, 0, 4, c->stream));
+  k_unique_flags<<<grid_for(m.nnz, 256, c->sm_count), 256, 0, c->stream>>>(m.nnz, sorted, flag);
+  CKR(exclusive_sum_u32(c, ar, flag, pos, m.nnz + 1));
+  uint32_t n_unique = 0;
+  CK(cudaMemcpyAsync(&n_unique, pos + m.nnz, 4, cudaMemcpyDeviceToHost, c->stream));
+  k_unique_scatter<<<grid_for(m.nnz, 256, c->sm_count), 256, 0, c->stream>>>(m.nnz, sorted, flag, pos, other, m.col);
+  CK(cudaStreamSynchronize(c->stream));
+  k_rowptr_from_keys<<<grid_for(m.n_rows + 1, 256, c->sm_count), 256, 0, c->stream>>>(m.n_rows, n_unique, other, m.rp);
+  c->launches += 3;
+  m.nnz = n_unique;
+  CK(cudaGetLastError());
+  ar.release(flag);
+  ar.release(pos);
+  ar.release(k0);
+  ar.release(k1);
+  return CCO_OK;
+}
+
+// sampleDownAndBinarize of one uploaded matrix (raw column counts already final in raw_counts)
+static int downsample_device(cco_ctx *c, Arena &ar, const DevRaw &raw, const int32_t *raw_counts, int32_t m,
+                             int32_t seed, uint32_t flags, DevMat *out) {
+  out->n_rows = raw.n_rows;
+  out->n_cols = raw.n_cols;
+  uint32_t *kept;
+  CKR(ar.alloc(&kept, raw.n_rows + 1));
+  CKR(ar.alloc(&out->rp, raw.n_rows + 1));
+  CKR(ar.alloc(&out->marg, std::max<int32_t>(raw.n_cols, 1)));
+  CKR(ar.alloc(&out->col, std::max<long long>(raw.nnz, 1)));
+  CK(cudaMemsetAsync(out->marg, 0, sizeof(int32_t) * std::max<int32_t>(raw.n_cols, 1), c->stream));
+  CK(cudaMemsetAsync(kept + raw.n_rows, 0, 4, c->stream));
+  int g = grid_for(raw.n_rows * kSG, 256, c->sm_count);
+  k_downsample_count<<<g, 256, 0, c->stream>>>(raw.n_rows, raw.rp, raw.col, raw_counts, m, seed, flags, kept, out->marg);
+  CKR(exclusive_sum_u32(c, ar, kept, out->rp, raw.n_rows + 1));
+  k_downsample_write<<<g, 256, 0, c->stream>>>(raw.n_rows, raw.rp, raw.col, raw_counts, m, seed, flags, out->rp, out->col);
+  c->launches += 2;
+  CK(cudaGetLastError());
+  ar.release(kept);
+  return CCO_OK;
+}
+
+// ---- row-kernel configurations -----------------------------------------------------------------
+struct BinCfg {
+  int threads;
+  int slots;
+  int cap;
+  int cbuf;
+  bool dense;
+  size_t smem;
+  int ctas_per_sm;
+};
+
+static int next_pow2(int x) {
+  int p = 1;
+  while (p < x) p <<= 1;
+  return p;
+}
+
+template <int THREADS>
+static int launch_rows_t(cco_ctx *c, const RowArgs &a, const BinCfg &cfg) {
+  int grid = c->sm_count * std::max(1, cfg.ctas_per_sm);
+  if (cfg.dense) {
+    CK(cudaFuncSetAttribute(k_rows<THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
+    k_rows<THREADS, true><<<grid, THREADS, cfg.smem, c->stream>>>(a);
+  } else {
+    CK(cudaFuncSetAttribute(k_rows<THREADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
+    k_rows<THREADS, false><<<grid, THREADS, cfg.smem, c->stream>>>(a);
+  }
+  c->launches++;
+  CK(cudaGetLastError());
+  return CCO_OK;
+}
+static int launch_rows(cco_ctx *c, const RowArgs &a, const BinCfg &cfg) {
+  switch (cfg.threads) {
+    case 1024: return launch_rows_t<1024>(c, a, cfg);
+    case 256: return launch_rows_t<256>(c, a, cfg);
+    case 64: return launch_rows_t<64>(c, a, cfg);
+  }
+  return set_error(CCO_E_INVALID_ARG, "internal: bad bin config");
+}
+
+static BinCfg make_cfg(cco_ctx *c, int threads, int want_slots, int top_k, int n_cols_b) {
+  BinCfg f;
+  f.threads = threads;
+  f.cbuf = next_pow2(std::max(2 * threads, top_k + threads));
+  size_t cand_bytes = (size_t)f.cbuf * 16;
+  size_t avail = c->smem_optin - 1024;  // static shared + slack
+  int max_slots = (int)((avail - cand_bytes) / 4);
+  f.slots = std::min(want_slots, max_slots);
+  f.cap = (int)(f.slots * 0.6);
+  f.dense = n_cols_b <= f.slots;
+  f.smem = cand_bytes + (size_t)f.slots * 4;
+  size_t per_sm = 228 * 1024;
+  f.ctas_per_sm = (int)std::min<size_t>(std::min<size_t>(per_sm / (f.smem + 1024), 2048 / threads), 32);
+  if (f.ctas_per_sm < 1) f.ctas_per_sm = 1;
+  return f;
+}
+
+struct IndicatorOut {
+  int64_t row_begin = 0, row_end = 0;
+  int64_t nnz = 0;
+  int64_t products = 0, distinct = 0;
+};
+
+// One indicator: rows [row_lo,row_hi) of A'^T B'.  Leaves the packed result in pinned host memory.
+static int run_indicator(cco_ctx *c, Arena &ar, const uint32_t *at_ptr, const int32_t *at_users, int32_t n_items_a,
+                         const int32_t *marg_a, int32_t max_marg_a, const DevMat &B, long long n_users, bool self,
+                         const cco_indicator_params_t &prm, uint32_t flags, bool emit_all, int rank, int world,
+                         ResultMat *rm, IndicatorOut *io, float *ms_rows) {
+  cudaStream_t s = c->stream;
+  const int32_t n_cols_b = B.n_cols;
+  // 1. work per output row + schedule ------------------------------------------------------------
+  uint32_t *row_work, *sorted_work;
+  unsigned long long *work64;
+  long long *work_prefix;
+  int32_t *ids, *rows_sorted;
+  CKR(ar.alloc(&row_work, n_items_a + 1));
+  CKR(ar.alloc(&work64, n_items_a + 1));
+  CKR(ar.alloc(&work_prefix, n_items_a + 1));
+  CKR(ar.alloc(&ids, n_items_a + 1));
+  CK(cudaMemsetAsync(work64 + n_items_a, 0, 8, s));
+  k_row_work<<<grid_for((long long)n_items_a * kSG, 256, c->sm_count), 256, 0, s>>>(n_items_a, at_ptr, at_users, B.rp,
+                                                                                 row_work, work64, ids);
+  c->launches++;
+  CKR(exclusive_sum_i64(c, ar, (const long long *)work64, work_prefix, (long long)n_items_a + 1));
+  // rank partition: contiguous item ranges balanced by work prefix (identical on every rank)
+  int32_t row_lo = 0, row_hi = n_items_a;
+  long long total_work = 0;
+  {
+    std::vector<long long> hp;
+    CK(cudaMemcpyAsync(&total_work, work_prefix + n_items_a, 8, cudaMemcpyDeviceToHost, s));
+    if (world > 1) {
+      hp.resize((size_t)n_items_a + 1);
+      CK(cudaMemcpyAsync(hp.data(), work_prefix, sizeof(long long) * ((size_t)n_items_a + 1), cudaMemcpyDeviceToHost, s));
+    }
+    CK(cudaStreamSynchronize(s));
+    if (world > 1) {
+      auto cut = [&](int r) -> int32_t {
+        if (r <= 0) return 0;
+        if (r >= world) return n_items_a;
+        // weight = products + a per-row constant so empty-work rows are spread too
+        long long target = (long long)((__int128)(total_work + n_items_a) * r / world);
+        int lo = 0, hi = n_items_a;
+        while (lo < hi) {
+          int mid = (lo + hi) >> 1;
+          if (hp[mid] + mid < target) lo = mid + 1; else hi = mid;
+        }
+        return lo;
+      };
+      row_lo = cut(rank);
+      row_hi = cut(rank + 1);
+    }
+  }
+  const int32_t n_my = row_hi - row_lo;
+  io->row_begin = row_lo;
+  io->row_end = row_hi;
+  {
+    long long hp2[2] = {0, 0};
+    CK(cudaMemcpyAsync(&hp2[0], work_prefix + row_lo, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&hp2[1], work_prefix + row_hi, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    io->products = hp2[1] - hp2[0];
+  }
+  CKR(ar.alloc(&sorted_work, n_my + 1));
+  CKR(ar.alloc(&rows_sorted, n_my + 1));
+  if (n_my > 0) {
+    size_t tb = 0;
+    CK(cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, row_work + row_lo, sorted_work, ids + row_lo, rows_sorted,
+                                                 n_my, 0, 32, s));
+    void *tmp;
+    CKR(ar.alloc((char **)&tmp, tb));
+    CK(cub::DeviceRadixSort::SortPairsDescending(tmp, tb, row_work + row_lo, sorted_work, ids + row_lo, rows_sorted, n_my,
+                                                 0, 32, s));
+    c->launches += 6;
+    ar.release(tmp);
+  }
+  // 2. bins -----------------------------------------------------------------------------------------
+  const int k_eff = emit_all ? 1 : prm.top_k;
+  BinCfg cfgL = make_cfg(c, 1024, 1 << 20, k_eff, n_cols_b);
+  BinCfg cfgM = make_cfg(c, 256, 8192, k_eff, n_cols_b);
+  BinCfg cfgS = make_cfg(c, 64, 1024, k_eff, n_cols_b);
+  // packed word: key bits must leave room for the largest possible count (= users of the item)
+  int key_bits = 1;
+  while (((1LL << key_bits) - 1) <= (long long)n_cols_b) ++key_bits;  // keys <= 2^kb - 2
+  int count_bits = 32 - key_bits;
+  bool any_hashed = !(cfgL.dense && cfgM.dense && cfgS.dense);
+  if (any_hashed && (count_bits < 1 || (long long)max_marg_a >= (1LL << count_bits)))
+    return set_error(CCO_E_UNSUPPORTED,
+                     "an item with %d users and %d columns does not fit the packed 32-bit accumulator word "
+                     "(key %d bits + count %d bits)", max_marg_a, n_cols_b, key_bits, count_bits);
+  // thresholds on w (descending): bin0 = multi-pass L, bin1 = L, bin2 = M, bin3 = S, tail = no work
+  auto thr = [&](const BinCfg &f) -> uint32_t { return (f.dense || n_cols_b <= f.cap) ? 0xffffffffu : (uint32_t)f.cap; };
+  // bins are chosen by WORK for parallelism; a config can only take rows whose distinct bound fits
+  uint32_t tL = thr(cfgL);
+  uint32_t tM = std::min<uint32_t>(thr(cfgM), 16384u);
+  uint32_t tS = std::min<uint32_t>(thr(cfgS), 1024u);
+  if (tM > tL) tM = tL;
+  if (tS > tM) tS = tM;
+  uint32_t h_thr[4] = {tL, tM, tS, 0u};
+  uint32_t *d_thr;
+  int32_t *d_bounds;
+  CKR(ar.alloc(&d_thr, 4));
+  CKR(ar.alloc(&d_bounds, 8));
+  CK(cudaMemcpyAsync(d_thr, h_thr, sizeof h_thr, cudaMemcpyHostToDevice, s));
+  k_bin_bounds<<<1, 32, 0, s>>>(n_my, sorted_work, 4, d_thr, d_bounds);
+  c->launches++;
+  // 3. outputs ----------------------------------------------------------------------------------------
+  int32_t stride = emit_all ? n_cols_b : std::min<int32_t>(prm.top_k, n_cols_b);
+  if (stride < 1) stride = 1;
+  int32_t *o_col, *o_cnt, *o_len;
+  double *o_llr = nullptr;
+  unsigned long long *d_distinct;
+  int *d_err;
+  size_t cells = (size_t)std::max(n_items_a, 1) * stride;
+  CKR(ar.alloc(&o_col, cells));
+  CKR(ar.alloc(&o_cnt, cells));
+  if (!emit_all) CKR(ar.alloc(&o_llr, cells));
+  CKR(ar.alloc(&o_len, n_items_a + 1));
+  CKR(ar.alloc(&d_distinct, 1));
+  CKR(ar.alloc(&d_err, 1));
+  CK(cudaMemsetAsync(o_len, 0, sizeof(int32_t) * ((size_t)n_items_a + 1), s));
+  CK(cudaMemsetAsync(d_distinct, 0, 8, s));
+  CK(cudaMemsetAsync(d_err, 0, 4, s));
+  RowArgs a;
+  memset(&a, 0, sizeof a);
+  a.at_ptr = at_ptr;
+  a.at_users = at_users;
+  a.b_ptr = B.rp;
+  a.b_col = B.col;
+  a.marg_a = marg_a;
+  a.marg_b = B.marg;
+  a.rows_sorted = rows_sorted;
+  a.row_work = row_work;
+  a.bin_bounds = d_bounds;
+  a.n_cols_b = n_cols_b;
+  a.n_users = n_users;
+  a.self = self ? 1 : 0;
+  a.top_k = k_eff;
+  a.has_min_llr = prm.has_min_llr;
+  a.min_llr = prm.min_llr;
+  a.flags = flags;
+  a.count_bits = count_bits;
+  a.out_stride = stride;
+  a.out_col = o_col;
+  a.out_llr = o_llr;
+  a.out_cnt = o_cnt;
+  a.out_len = o_len;
+  a.stat_distinct = d_distinct;
+  a.err_flag = d_err;
+  a.emit_all = emit_all ? 1 : 0;
+  CK(cudaEventRecord(c->ev[4], s));
+  if (n_my > 0) {
+    const BinCfg *cfgs[4] = {&cfgL, &cfgL, &cfgM, &cfgS};
+    for (int b = 0; b < 4; ++b) {
+      RowArgs ab = a;
+      ab.bin = b;
+      ab.slots = cfgs[b]->slots;
+      ab.cap = cfgs[b]->cap;
+      ab.cbuf = cfgs[b]->cbuf;
+      if (b == 0 && cfgL.dense) continue;  // dense L takes every large row in bin 1 (threshold = max)
+      CKR(launch_rows(c, ab, *cfgs[b]));
+    }
+  }
+  CK(cudaEventRecord(c->ev[5], s));
+  // 4. pack + copy back ---------------------------------------------------------------------------------
+  long long *len64, *out_ptr;
+  CKR(ar.alloc(&len64, n_my + 1));
+  CKR(ar.alloc(&out_ptr, n_my + 1));
+  CK(cudaMemsetAsync(len64 + n_my, 0, 8, s));
+  if (n_my > 0) {
+    k_len_to_i64<<<grid_for(n_my, 256, c->sm_count), 256, 0, s>>>(row_lo, n_my, o_len, len64);
+    c->launches++;
+  }
+  CKR(exclusive_sum_i64(c, ar, len64, out_ptr, (long long)n_my + 1));
+  long long total = 0;
+  unsigned long long h_distinct = 0;
+  int h_err = 0;
+  CK(cudaMemcpyAsync(&total, out_ptr + n_my, 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(&h_distinct, d_distinct, 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(&h_err, d_err, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (h_err) return set_error(CCO_E_CUDA, "internal: shared-memory hash table overflow");
+  io->nnz = total;
+  io->distinct = (int64_t)h_distinct;
+  int32_t *p_col, *p_cnt;
+  double *p_llr = nullptr;
+  CKR(ar.alloc(&p_col, std::max<long long>(total, 1)));
+  CKR(ar.alloc(&p_cnt, std::max<long long>(total, 1)));
+  if (!emit_all) CKR(ar.alloc(&p_llr, std::max<long long>(total, 1)));
+  if (n_my > 0 && total > 0) {
+    k_compact_rows<<<grid_for((long long)n_my * 32, 256, c->sm_count), 256, 0, s>>>(row_lo, n_my, stride, out_ptr, o_len,
+                                                                                 o_col, o_llr, o_cnt, p_col, p_llr, p_cnt);
+    c->launches++;
+  }
+  rm->row_begin = row_lo;
+  rm->row_end = row_hi;
+  rm->n_cols = n_cols_b;
+  rm->row_ptr = (int64_t *)c->pinned_get(sizeof(int64_t) * ((size_t)n_my + 1));
+  rm->col = (int32_t *)c->pinned_get(sizeof(int32_t) * (size_t)std::max<long long>(total, 1));
+  rm->cnt = (int32_t *)c->pinned_get(sizeof(int32_t) * (size_t)std::max<long long>(total, 1));
+  rm->llr = (double *)c->pinned_get(sizeof(double) * (size_t)std::max<long long>(total, 1));
+  if (!rm->row_ptr || !rm->col || !rm->cnt || !rm->llr) return set_error(CCO_E_OOM, "pinned host allocation failed");
+  CK(cudaMemcpyAsync(rm->row_ptr, out_ptr, sizeof(int64_t) * ((size_t)n_my + 1), cudaMemcpyDeviceToHost, s));
+  if (total > 0) {
+    CK(cudaMemcpyAsync(rm->col, p_col, sizeof(int32_t) * (size_t)total, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(rm->cnt, p_cnt, sizeof(int32_t) * (size_t)total, cudaMemcpyDeviceToHost, s));
+    if (!emit_all) CK(cudaMemcpyAsync(rm->llr, p_llr, sizeof(double) * (size_t)total, cudaMemcpyDeviceToHost, s));
+  }
+  CK(cudaStreamSynchronize(s));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]));
+  if (ms_rows) *ms_rows = ms;
+  // release the big per-indicator buffers early
+  for (void *p : {(void *)o_col, (void *)o_cnt, (void *)o_llr, (void *)p_col, (void *)p_cnt, (void *)p_llr})
+    if (p) ar.release(p);
+  return CCO_OK;
+}
+
+static int validate_host(int32_t n_mats, const cco_csr_t *mats, const cco_indicator_params_t *params) {
+  if (n_mats < 1 || !mats || !params) return set_error(CCO_E_INVALID_ARG, "need at least the primary matrix and its params");
+  for (int i = 0; i < n_mats; ++i) {
+    const cco_csr_t &m = mats[i];
+    if (!m.row_ptr) return set_error(CCO_E_INVALID_ARG, "matrix %d: null row_ptr", i);
+    if (m.n_rows < 0 || m.n_rows >= 0x7fffffffLL) return set_error(CCO_E_INVALID_ARG, "matrix %d: n_rows out of range", i);
+    if (m.n_cols < 0 || m.n_cols >= 0x7ffffffe) return set_error(CCO_E_INVALID_ARG, "matrix %d: n_cols out of range", i);
+    if (m.n_rows != mats[0].n_rows)
+      return set_error(CCO_E_SHAPE_MISMATCH, "matrix %d has %lld rows, the primary has %lld: all event types share the user dictionary",
+                       i, (long long)m.n_rows, (long long)mats[0].n_rows);
+    if (m.row_ptr[0] != 0) return set_error(CCO_E_INVALID_ARG, "matrix %d: row_ptr[0] != 0", i);
+    long long nnz = m.row_ptr[m.n_rows];
+    if (nnz < 0 || nnz >= 0xffffffffLL) return set_error(CCO_E_UNSUPPORTED, "matrix %d: nnz %lld outside [0, 2^32)", i, nnz);
+    if (nnz > 0 && !m.col_idx) return set_error(CCO_E_INVALID_ARG, "matrix %d: null col_idx", i);
+    if (params[i].max_interactions < 1) return set_error(CCO_E_INVALID_ARG, "matrix %d: max_interactions must be >= 1", i);
+    if (params[i].top_k < 1) return set_error(CCO_E_INVALID_ARG, "matrix %d: top_k must be >= 1", i);
+    if (params[i].top_k > CCO_MAX_TOP_K)
+      return set_error(CCO_E_UNSUPPORTED, "matrix %d: top_k %d > CCO_MAX_TOP_K (%d)", i, params[i].top_k, CCO_MAX_TOP_K);
+    if (params[i].has_min_llr && params[i].min_llr != params[i].min_llr)
+      return set_error(CCO_E_INVALID_ARG, "matrix %d: min_llr is NaN", i);
+  }
+  return CCO_OK;
+}
+
+static int upload(cco_ctx *c, Arena &ar, const cco_csr_t &m, DevRaw *d) {
+  d->n_rows = m.n_rows;
+  d->n_cols = m.n_cols;
+  d->nnz = m.row_ptr[m.n_rows];
+  CKR(ar.alloc(&d->rp, m.n_rows + 1));
+  CKR(ar.alloc(&d->col, std::max<long long>(d->nnz, 1)));
+  CK(cudaMemcpyAsync(d->rp, m.row_ptr, sizeof(int64_t) * ((size_t)m.n_rows + 1), cudaMemcpyHostToDevice, c->stream));
+  if (d->nnz > 0)
+    CK(cudaMemcpyAsync(d->col, m.col_idx, sizeof(int32_t) * (size_t)d->nnz, cudaMemcpyHostToDevice, c->stream));
+  return CCO_OK;
+}
+
+// check + (if needed) canonicalise every uploaded matrix
+static int check_and_canonicalize(cco_ctx *c, Arena &ar, std::vector<DevRaw> &raw, uint32_t flags) {
+  if (flags & CCO_FLAG_ASSUME_CANONICAL) return CCO_OK;
+  int n = (int)raw.size();
+  int *d_flags;
+  CKR(ar.alloc(&d_flags, 2 * n));
+  CK(cudaMemsetAsync(d_flags, 0, sizeof(int) * 2 * n, c->stream));
+  for (int i = 0; i < n; ++i) {
+    k_check_rows<<<grid_for(raw[i].n_rows * kSG, 256, c->sm_count), 256, 0, c->stream>>>(raw[i].n_rows, raw[i].n_cols,
+                                                                                      raw[i].rp, raw[i].col, d_flags + 2 * i);
+    c->launches++;
+  }
+  std::vector<int> h(2 * n);
+  CK(cudaMemcpyAsync(h.data(), d_flags, sizeof(int) * 2 * n, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaGetLastError());
+  for (int i = 0; i < n; ++i)
+    if (h[2 * i]) return set_error(CCO_E_INVALID_ARG, "matrix %d: row_ptr not monotone or column index out of [0, n_cols)", i);
+  for (int i = 0; i < n; ++i)
+    if (h[2 * i + 1]) CKR(canonicalize_device(c, ar, raw[i]));
+  return CCO_OK;
+}
+
+static int train_impl(cco_ctx *c, int32_t n_mats, const cco_csr_t *mats, const cco_indicator_params_t *params, int32_t seed,
+                      uint32_t flags, cco_result **out) {
+  CKR(validate_host(n_mats, mats, params));
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  Arena ar(s);
+  c->launches = 0;
+  cco_result *res = new cco_result();
+  res->ctx = c;
+  res->mats.resize(n_mats);
+  memset(&res->stats, 0, sizeof res->stats);
+  struct Guard {
+    cco_result *r;
+    bool ok = false;
+    ~Guard() {
+      if (!ok) cco_result_free(r);
+    }
+  } guard{res};
+  cco_stats_t &st = res->stats;
+  st.n_mats = n_mats;
+  st.n_users = mats[0].n_rows;
+  const long long n_users = mats[0].n_rows;
+
+  CK(cudaEventRecord(c->ev[0], s));
+  std::vector<DevRaw> raw(n_mats);
+  for (int i = 0; i < n_mats; ++i) {
+    CKR(upload(c, ar, mats[i], &raw[i]));
+    st.nnz_in_total += raw[i].nnz;
+  }
+  CK(cudaEventRecord(c->ev[1], s));
+  CKR(check_and_canonicalize(c, ar, raw, flags));
+  // raw column counts: this rank histograms its user slice; ONE allreduce sums all matrices' counts
+  long long total_cols = 0;
+  std::vector<long long> col_off(n_mats + 1, 0);
+  for (int i = 0; i < n_mats; ++i) {
+    col_off[i] = total_cols;
+    total_cols += raw[i].n_cols;
+  }
+  col_off[n_mats] = total_cols;
+  int32_t *raw_counts;
+  CKR(ar.alloc(&raw_counts, std::max<long long>(total_cols, 1)));
+  CK(cudaMemsetAsync(raw_counts, 0, sizeof(int32_t) * (size_t)std::max<long long>(total_cols, 1), s));
+  const long long u_lo = n_users * c->rank / c->world, u_hi = n_users * (c->rank + 1) / c->world;
+  for (int i = 0; i < n_mats; ++i) {
+    if (raw[i].nnz == 0 || u_hi == u_lo) continue;
+    k_col_histogram<<<grid_for(raw[i].nnz / c->world + 1, 256, c->sm_count), 256, 0, s>>>(u_lo, u_hi, raw[i].rp, raw[i].col,
+                                                                                       raw_counts + col_off[i]);
+    c->launches++;
+  }
+  if (c->world > 1) {
+    int r = g_nccl.AllReduce(raw_counts, raw_counts, (size_t)total_cols, kNcclInt32, kNcclSum, c->comm, s);
+    if (r != 0) return set_error(CCO_E_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString(r));
+  }
+  // sampleDownAndBinarize every matrix
+  std::vector<DevMat> dm(n_mats);
+  for (int i = 0; i < n_mats; ++i) {
+    CKR(downsample_device(c, ar, raw[i], raw_counts + col_off[i], params[i].max_interactions, seed, flags, &dm[i]));
+    ar.release(raw[i].col);
+    ar.release(raw[i].rp);
+  }
+  // `drmA.t`
+  const int32_t n_items_a = dm[0].n_cols;
+  uint32_t *at_ptr, *cursor;
+  int32_t *at_users, *d_max;
+  CKR(ar.alloc(&at_ptr, n_items_a + 1));
+  CKR(ar.alloc(&cursor, n_items_a + 1));
+  CKR(ar.alloc(&d_max, 1));
+  CKR(ar.alloc(&at_users, std::max<long long>(raw[0].nnz, 1)));
+  CK(cudaMemsetAsync(d_max, 0, 4, s));
+  {
+    // at_ptr = exclusive scan of colA; the scan reads one element past the end -> pad explicitly
+    uint32_t *marg_pad;
+    CKR(ar.alloc(&marg_pad, n_items_a + 1));
+    CK(cudaMemcpyAsync(marg_pad, dm[0].marg, sizeof(int32_t) * (size_t)n_items_a, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemsetAsync(marg_pad + n_items_a, 0, 4, s));
+    CKR(exclusive_sum_u32(c, ar, marg_pad, at_ptr, (long long)n_items_a + 1));
+    ar.release(marg_pad);
+  }
+  CK(cudaMemcpyAsync(cursor, at_ptr, sizeof(uint32_t) * ((size_t)n_items_a + 1), cudaMemcpyDeviceToDevice, s));
+  k_transpose_scatter<<<grid_for(n_users * kSG, 256, c->sm_count), 256, 0, s>>>(n_users, dm[0].rp, dm[0].col, cursor, at_users);
+  if (n_items_a > 0) k_max_i32<<<grid_for(n_items_a, 256, c->sm_count, 2), 256, 0, s>>>(n_items_a, dm[0].marg, d_max);
+  c->launches += 2;
+  int32_t max_marg_a = 0;
+  std::vector<uint32_t> h_nnz(n_mats);
+  CK(cudaMemcpyAsync(&max_marg_a, d_max, 4, cudaMemcpyDeviceToHost, s));
+  for (int i = 0; i < n_mats; ++i)
+    CK(cudaMemcpyAsync(&h_nnz[i], dm[i].rp + n_users, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaEventRecord(c->ev[2], s));
+  CK(cudaStreamSynchronize(s));
+  CK(cudaGetLastError());
+  for (int i = 0; i < n_mats && i < 16; ++i) st.nnz_downsampled[i] = h_nnz[i];
+
+  for (int i = 0; i < n_mats; ++i) {
+    IndicatorOut io;
+    float ms_rows = 0;
+    CKR(run_indicator(c, ar, at_ptr, at_users, n_items_a, dm[0].marg, max_marg_a, dm[i], n_users, i == 0, params[i], flags,
+                      false, c->rank, c->world, &res->mats[i], &io, &ms_rows));
+    if (i < 16) {
+      st.products[i] = io.products;
+      st.distinct_cells[i] = io.distinct;
+      st.out_nnz[i] = io.nnz;
+      st.ms_indicator[i] = ms_rows;
+    }
+  }
+  CK(cudaEventRecord(c->ev[3], s));
+  CK(cudaStreamSynchronize(s));
+  CK(cudaEventElapsedTime(&st.ms_h2d, c->ev[0], c->ev[1]));
+  CK(cudaEventElapsedTime(&st.ms_prepare, c->ev[1], c->ev[2]));
+  CK(cudaEventElapsedTime(&st.ms_cooccurrence, c->ev[2], c->ev[3]));
+  CK(cudaEventElapsedTime(&st.ms_total, c->ev[0], c->ev[3]));
+  st.n_kernel_launches = c->launches;
+  guard.ok = true;
+  *out = res;
+  return CCO_OK;
+}
+
+}  // namespace cco
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+int cco_abi_version(void) { return CCO_ABI_VERSION; }
+const char *cco_last_error(void) { return g_err; }
+const char *cco_status_string(int s) {
+  switch (s) {
+    case CCO_OK: return "ok";
+    case CCO_E_INVALID_ARG: return "invalid argument";
+    case CCO_E_CUDA: return "CUDA error";
+    case CCO_E_NCCL: return "NCCL error";
+    case CCO_E_OOM: return "out of memory";
+    case CCO_E_SHAPE_MISMATCH: return "shape mismatch";
+    case CCO_E_UNSUPPORTED: return "unsupported";
+  }
+  return "unknown";
+}
+
+int cco_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) return set_error(CCO_E_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+  int ok = 0;
+  for (int i = 0; i < n; ++i) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ++ok;
+  }
+  return ok;
+}
+
+int cco_nccl_unique_id(unsigned char out[128]) {
+  if (!out) return set_error(CCO_E_INVALID_ARG, "null output");
+  CKR(load_nccl());
+  ncclUniqueId id;
+  int r = g_nccl.GetUniqueId(&id);
+  if (r != 0) return set_error(CCO_E_NCCL, "ncclGetUniqueId: %s", g_nccl.GetErrorString(r));
+  memcpy(out, id.internal, 128);
+  return CCO_OK;
+}
+
+int cco_create(const cco_config_t *cfg, cco_ctx_t **out) {
+  if (!cfg || !out) return set_error(CCO_E_INVALID_ARG, "null argument");
+  if (cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size)
+    return set_error(CCO_E_INVALID_ARG, "bad rank/world_size %d/%d", cfg->rank, cfg->world_size);
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return set_error(CCO_E_CUDA, "no CUDA device (%s): this library has no CPU fallback",
+                     e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  if (cfg->device < 0 || cfg->device >= n) return set_error(CCO_E_INVALID_ARG, "device %d not in [0,%d)", cfg->device, n);
+  cudaDeviceProp p;
+  CK(cudaGetDeviceProperties(&p, cfg->device));
+  if (p.major != 10)
+    return set_error(CCO_E_CUDA, "device %d is sm_%d%d; this build contains sm_100a code only", cfg->device, p.major, p.minor);
+  CK(cudaSetDevice(cfg->device));
+  cco_ctx *c = new cco_ctx();
+  c->device = cfg->device;
+  c->rank = cfg->rank;
+  c->world = cfg->world_size;
+  c->sm_count = p.multiProcessorCount;
+  c->smem_optin = p.sharedMemPerBlockOptin;
+  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  for (auto &ev : c->ev) CK(cudaEventCreate(&ev));
+  cudaMemPool_t pool;
+  CK(cudaDeviceGetDefaultMemPool(&pool, cfg->device));
+  uint64_t thr = UINT64_MAX;
+  CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  if (c->world > 1) {
+    if (!cfg->nccl_unique_id) {
+      delete c;
+      return set_error(CCO_E_INVALID_ARG, "world_size > 1 needs nccl_unique_id");
+    }
+    int r = load_nccl();
+    if (r != CCO_OK) {
+      delete c;
+      return r;
+    }
+    ncclUniqueId id;
+    memcpy(id.internal, cfg->nccl_unique_id, 128);
+    int rc = g_nccl.CommInitRank(&c->comm, c->world, id, c->rank);
+    if (rc != 0) {
+      delete c;
+      return set_error(CCO_E_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString(rc));
+    }
+  }
+  *out = c;
+  return CCO_OK;
+}
+
+int cco_destroy(cco_ctx_t *c) {
+  if (!c) return CCO_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (c->comm) g_nccl.CommDestroy(c->comm);
+  for (auto &b : c->pinned) cudaFreeHost(b.p);
+  for (auto &ev : c->ev)
+    if (ev) cudaEventDestroy(ev);
+  cudaStreamDestroy(c->stream);
+  cudaStreamDestroy(c->copy_stream);
+  delete c;
+  return CCO_OK;
+}
+
+int cco_host_alloc(cco_ctx_t *c, size_t bytes, void **out) {
+  if (!c || !out) return set_error(CCO_E_INVALID_ARG, "null argument");
+  CK(cudaSetDevice(c->device));
+  void *p = c->pinned_get(bytes);
+  if (!p) return set_error(CCO_E_OOM, "cudaHostAlloc(%zu) failed", bytes);
+  *out = p;
+  return CCO_OK;
+}
+int cco_host_free(cco_ctx_t *c, void *p) {
+  if (!c) return set_error(CCO_E_INVALID_ARG, "null context");
+  if (p) c->pinned_put(p);
+  return CCO_OK;
+}
+
+int cco_train(cco_ctx_t *ctx, int32_t n_mats, const cco_csr_t *mats, const cco_indicator_params_t *params, int32_t seed,
+              uint32_t flags, cco_result_t **out) {
+  if (!ctx || !out) return set_error(CCO_E_INVALID_ARG, "null argument");
+  *out = nullptr;
+  return train_impl(ctx, n_mats, mats, params, seed, flags, out);
+}
+
+int cco_cooccurrences_idss(cco_ctx_t *ctx, int32_t n_mats, const cco_csr_t *mats, int32_t seed,
+                           int32_t max_interesting_items_per_thing, int32_t max_num_interactions, uint32_t flags,
+                           cco_result_t **out) {
+  if (n_mats < 1) return set_error(CCO_E_INVALID_ARG, "need at least the primary matrix");
+  std::vector<cco_indicator_params_t> p(n_mats);
+  for (auto &q : p) {
+    q.max_interactions = max_num_interactions;
+    q.top_k = max_interesting_items_per_thing;
+    q.has_min_llr = 0;
+    q.min_llr = 0.0;
+  }
+  return cco_train(ctx, n_mats, mats, p.data(), seed, flags, out);
+}
+
+int cco_result_num_matrices(const cco_result_t *r) { return r ? (int)r->mats.size() : set_error(CCO_E_INVALID_ARG, "null result"); }
+
+int cco_result_row_range(const cco_result_t *r, int32_t i, int64_t *row_begin, int64_t *row_end) {
+  if (!r || i < 0 || i >= (int)r->mats.size()) return set_error(CCO_E_INVALID_ARG, "bad result/index");
+  if (row_begin) *row_begin = r->mats[i].row_begin;
+  if (row_end) *row_end = r->mats[i].row_end;
+  return CCO_OK;
+}
+
+int cco_result_matrix(const cco_result_t *r, int32_t i, int64_t *n_rows, int32_t *n_cols, const int64_t **row_ptr,
+                      const int32_t **col_idx, const double **llr, const int32_t **count) {
+  if (!r || i < 0 || i >= (int)r->mats.size()) return set_error(CCO_E_INVALID_ARG, "bad result/index");
+  const ResultMat &m = r->mats[i];
+  if (n_rows) *n_rows = m.row_end - m.row_begin;
+  if (n_cols) *n_cols = m.n_cols;
+  if (row_ptr) *row_ptr = m.row_ptr;
+  if (col_idx) *col_idx = m.col;
+  if (llr) *llr = m.llr;
+  if (count) *count = m.cnt;
+  return CCO_OK;
+}
+
+int cco_result_stats(const cco_result_t *r, cco_stats_t *out) {
+  if (!r || !out) return set_error(CCO_E_INVALID_ARG, "null argument");
+  *out = r->stats;
+  return CCO_OK;
+}
+
+int cco_result_free(cco_result_t *r) {
+  if (!r) return CCO_OK;
+  for (auto &m : r->mats) {
+    for (void *p : {(void *)m.row_ptr, (void *)m.col, (void *)m.llr, (void *)m.cnt})
+      if (p) r->ctx->pinned_put(p);
+  }
+  delete r;
+  return CCO_OK;
+}
+
+void cco_free(void *p) { free(p); }
+
+// ---- debug / parity entries ------------------------------------------------------------------------
+int cco_debug_llr(cco_ctx_t *c, int64_t n, const int64_t *k11, const int64_t *k12, const int64_t *k21, const int64_t *k22,
+                  uint32_t flags, double *out) {
+  if (!c || n < 0 || (n > 0 && (!k11 || !k12 || !k21 || !k22 || !out))) return set_error(CCO_E_INVALID_ARG, "bad argument");
+  if (n == 0) return CCO_OK;
+  for (int64_t i = 0; i < n; ++i)
+    if (k11[i] < 0 || k12[i] < 0 || k21[i] < 0 || k22[i] < 0)
+      return set_error(CCO_E_INVALID_ARG, "negative count at %lld (Preconditions.checkArgument in LogLikelihood)", (long long)i);
+  CK(cudaSetDevice(c->device));
+  Arena ar(c->stream);
+  long long *d[4];
+  double *dout;
+  const int64_t *h[4] = {k11, k12, k21, k22};
+  for (int j = 0; j < 4; ++j) {
+    CKR(ar.alloc(&d[j], n));
+    CK(cudaMemcpyAsync(d[j], h[j], sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  }
+  CKR(ar.alloc(&dout, n));
+  k_debug_llr<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, d[0], d[1], d[2], d[3], flags, dout);
+  CK(cudaMemcpyAsync(out, dout, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaGetLastError());
+  return CCO_OK;
+}
+
+int cco_debug_downsample(cco_ctx_t *c, const cco_csr_t *m, int32_t max_interactions, int32_t seed, uint32_t flags,
+                         int64_t **row_ptr, int32_t **col_idx, int32_t *raw_col_counts, int32_t *new_col_counts) {
+  if (!c || !m || !row_ptr || !col_idx) return set_error(CCO_E_INVALID_ARG, "null argument");
+  cco_indicator_params_t prm = {max_interactions, 1, 0, 0.0};
+  CKR(validate_host(1, m, &prm));
+  CK(cudaSetDevice(c->device));
+  Arena ar(c->stream);
+  std::vector<DevRaw> raw(1);
+  CKR(upload(c, ar, *m, &raw[0]));
+  CKR(check_and_canonicalize(c, ar, raw, flags));
+  int32_t *counts;
+  CKR(ar.alloc(&counts, std::max<int32_t>(m->n_cols, 1)));
+  CK(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)std::max<int32_t>(m->n_cols, 1), c->stream));
+  if (raw[0].nnz > 0 && m->n_rows > 0)
+    k_col_histogram<<<grid_for(raw[0].nnz, 256, c->sm_count), 256, 0, c->stream>>>(0, m->n_rows, raw[0].rp, raw[0].col, counts);
+  DevMat dm;
+  CKR(downsample_device(c, ar, raw[0], counts, max_interactions, seed, flags, &dm));
+  std::vector<uint32_t> rp32((size_t)m->n_rows + 1);
+  CK(cudaMemcpyAsync(rp32.data(), dm.rp, sizeof(uint32_t) * rp32.size(), cudaMemcpyDeviceToHost, c->stream));
+  if (raw_col_counts && m->n_cols > 0)
+    CK(cudaMemcpyAsync(raw_col_counts, counts, sizeof(int32_t) * (size_t)m->n_cols, cudaMemcpyDeviceToHost, c->stream));
+  if (new_col_counts && m->n_cols > 0)
+    CK(cudaMemcpyAsync(new_col_counts, dm.marg, sizeof(int32_t) * (size_t)m->n_cols, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaGetLastError());
+  size_t nnz = rp32[m->n_rows];
+  int64_t *rp = (int64_t *)malloc(sizeof(int64_t) * rp32.size());
+  int32_t *ci = (int32_t *)malloc(sizeof(int32_t) * std::max<size_t>(nnz, 1));
+  if (!rp || !ci) return set_error(CCO_E_OOM, "malloc failed");
+  for (size_t i = 0; i < rp32.size(); ++i) rp[i] = rp32[i];
+  if (nnz) CK(cudaMemcpy(ci, dm.col, sizeof(int32_t) * nnz, cudaMemcpyDeviceToHost));
+  *row_ptr = rp;
+  *col_idx = ci;
+  return CCO_OK;
+}
+
+int cco_debug_cooccurrence(cco_ctx_t *c, const cco_csr_t *a, const cco_csr_t *b, int64_t **row_ptr, int32_t **col_idx,
+                           int32_t **count) {
+  if (!c || !a || !b || !row_ptr || !col_idx || !count) return set_error(CCO_E_INVALID_ARG, "null argument");
+  cco_csr_t two[2] = {*a, *b};
+  cco_indicator_params_t prm[2] = {{0x7fffffff, 1, 0, 0.0}, {0x7fffffff, 1, 0, 0.0}};
+  CKR(validate_host(2, two, prm));
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  Arena ar(s);
+  std::vector<DevRaw> raw(2);
+  CKR(upload(c, ar, two[0], &raw[0]));
+  CKR(upload(c, ar, two[1], &raw[1]));
+  CKR(check_and_canonicalize(c, ar, raw, 0));
+  // identity "downsample" (m = INT_MAX) gives the device CSR + marginals
+  std::vector<DevMat> dm(2);
+  for (int i = 0; i < 2; ++i) {
+    int32_t *counts;
+    CKR(ar.alloc(&counts, std::max<int32_t>(raw[i].n_cols, 1)));
+    CK(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)std::max<int32_t>(raw[i].n_cols, 1), s));
+    if (raw[i].nnz > 0 && raw[i].n_rows > 0)
+      k_col_histogram<<<grid_for(raw[i].nnz, 256, c->sm_count), 256, 0, s>>>(0, raw[i].n_rows, raw[i].rp, raw[i].col, counts);
+    CKR(downsample_device(c, ar, raw[i], counts, 0x7fffffff, 0, 0, &dm[i]));
+  }
+  const int32_t n_items_a = dm[0].n_cols;
+  uint32_t *at_ptr, *cursor, *marg_pad;
+  int32_t *at_users, *d_max;
+  CKR(ar.alloc(&at_ptr, n_items_a + 1));
+  CKR(ar.alloc(&cursor, n_items_a + 1));
+  CKR(ar.alloc(&marg_pad, n_items_a + 1));
+  CKR(ar.alloc(&d_max, 1));
+  CKR(ar.alloc(&at_users, std::max<long long>(raw[0].nnz, 1)));
+  CK(cudaMemsetAsync(d_max, 0, 4, s));
+  CK(cudaMemcpyAsync(marg_pad, dm[0].marg, sizeof(int32_t) * (size_t)n_items_a, cudaMemcpyDeviceToDevice, s));
+  CK(cudaMemsetAsync(marg_pad + n_items_a, 0, 4, s));
+  CKR(exclusive_sum_u32(c, ar, marg_pad, at_ptr, (long long)n_items_a + 1));
+  CK(cudaMemcpyAsync(cursor, at_ptr, sizeof(uint32_t) * ((size_t)n_items_a + 1), cudaMemcpyDeviceToDevice, s));
+  k_transpose_scatter<<<grid_for(a->n_rows * kSG, 256, c->sm_count), 256, 0, s>>>(a->n_rows, dm[0].rp, dm[0].col, cursor, at_users);
+  if (n_items_a > 0) k_max_i32<<<grid_for(n_items_a, 256, c->sm_count, 2), 256, 0, s>>>(n_items_a, dm[0].marg, d_max);
+  int32_t max_marg_a = 0;
+  CK(cudaMemcpyAsync(&max_marg_a, d_max, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  CK(cudaGetLastError());
+  ResultMat rm;
+  IndicatorOut io;
+  cco_indicator_params_t p1 = {0x7fffffff, 1, 0, 0.0};
+  int rc = run_indicator(c, ar, at_ptr, at_users, n_items_a, dm[0].marg, max_marg_a, dm[1], a->n_rows, false, p1, 0, true, 0, 1,
+                         &rm, &io, nullptr);
+  auto put = [&]() {
+    for (void *p : {(void *)rm.row_ptr, (void *)rm.col, (void *)rm.llr, (void *)rm.cnt})
+      if (p) c->pinned_put(p);
+  };
+  if (rc != CCO_OK) {
+    put();
+    return rc;
+  }
+  size_t nnz = (size_t)rm.row_ptr[n_items_a];
+  int64_t *rp = (int64_t *)malloc(sizeof(int64_t) * ((size_t)n_items_a + 1));
+  int32_t *ci = (int32_t *)malloc(sizeof(int32_t) * std::max<size_t>(nnz, 1));
+  int32_t *cn = (int32_t *)malloc(sizeof(int32_t) * std::max<size_t>(nnz, 1));
+  if (!rp || !ci || !cn) {
+    put();
+    return set_error(CCO_E_OOM, "malloc failed");
+  }
+  memcpy(rp, rm.row_ptr, sizeof(int64_t) * ((size_t)n_items_a + 1));
+  // cells of a row come back in table order: sort each row by column for the caller
+  std::vector<std::pair<int32_t, int32_t>> tmp;
+  for (int32_t r = 0; r < n_items_a; ++r) {
+    size_t lo = (size_t)rp[r], hi = (size_t)rp[r + 1];
+    tmp.resize(hi - lo);
+    for (size_t q = lo; q < hi; ++q) tmp[q - lo] = {rm.col[q], rm.cnt[q]};
+    std::sort(tmp.begin(), tmp.end());
+    for (size_t q = lo; q < hi; ++q) {
+      ci[q] = tmp[q - lo].first;
+      cn[q] = tmp[q - lo].second;
+    }
+  }
+  put();
+  *row_ptr = rp;
+  *col_idx = ci;
+  *count = cn;
+  return CCO_OK;
+}
+
+}  // extern "C"

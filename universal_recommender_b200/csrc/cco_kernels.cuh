@@ -1,0 +1,570 @@
+// cco_kernels.cuh -- hand-written sm_100a kernels of the CCO train hot path.
+//
+// Reference semantics (what each stage replaces) -- Apache Mahout 0.13.0 SimilarityAnalysis,
+// called from /root/reference/src/main/scala/URAlgorithm.scala:323-329,343-346:
+//   H2 sampleDownAndBinarize  -> k_downsample_count / k_downsample_write
+//   H3 numNonZeroElementsPerColumn -> k_scan_rows (raw) + k_downsample_count (post-sample)
+//   `drmA.t`                  -> k_transpose_scatter
+//   H4 A'^T B' counts, H5 LLR, H6 top-k -> k_rows<> (one fused kernel, nothing materialised)
+//
+// Everything here is integer/byte work plus scalar fp64; no tensor cores (DESIGN.md "Roofline").
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cco {
+
+// ------------------------------------------------------------------------------------------------
+// device views
+// ------------------------------------------------------------------------------------------------
+struct RowArgs {
+  // A'^T: users of every primary item
+  const uint32_t *at_ptr;
+  const int32_t *at_users;
+  // B' (CSR over users)
+  const uint32_t *b_ptr;
+  const int32_t *b_col;
+  const int32_t *marg_a;  // colA, downsampled, per primary item
+  const int32_t *marg_b;  // colB, downsampled, per column of B'
+  // schedule: items sorted by estimated work, descending; bin b = rows_sorted[bin_bounds[b], bin_bounds[b+1])
+  const int32_t *rows_sorted;
+  const uint32_t *row_work;  // by item: w_a = sum_{u in a} degB'(u), saturated at 2^32-1
+  const int32_t *bin_bounds;
+  int32_t bin;
+  int32_t n_cols_b;
+  long long n_users;  // N
+  int32_t self;       // A'^T A': skip the diagonal
+  int32_t top_k;
+  int32_t has_min_llr;
+  double min_llr;
+  uint32_t flags;
+  int32_t count_bits;  // packed hash word = (key << count_bits) | count
+  int32_t slots;       // hash/dense table words in shared memory
+  int32_t cap;         // max distinct keys per pass for hashed rows (load-factor bound)
+  int32_t cbuf;        // candidate buffer entries (power of two, >= 2*top_k)
+  // outputs, strided
+  int32_t out_stride;
+  int32_t *out_col;
+  double *out_llr;
+  int32_t *out_cnt;
+  int32_t *out_len;
+  unsigned long long *stat_distinct;
+  int *err_flag;     // set to 1 if a hash table overflowed (result invalid)
+  int32_t emit_all;  // debug: write every non-zero cell (col,count), no LLR/top-k
+};
+
+constexpr uint32_t kEmpty = 0xffffffffu;
+
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z ^= z >> 30;
+  z *= 0xbf58476d1ce4e5b9ULL;
+  z ^= z >> 27;
+  z *= 0x94d049bb133111ebULL;
+  z ^= z >> 31;
+  return z;
+}
+// sampler of include/cco_b200.h "Sampler" (bit-identical to oracle/cco_oracle.c orc_hash64/orc_u01)
+__device__ __forceinline__ double sample_u01(int32_t seed, uint32_t u, uint32_t j) {
+  uint64_t x = mix64(((uint64_t)(uint32_t)seed << 32) | (uint64_t)u);
+  uint64_t h = mix64(x + (uint64_t)j * 0x9e3779b97f4a7c15ULL);
+  return __dmul_rn((double)(h >> 11), 0x1.0p-53);
+}
+__device__ __forceinline__ uint32_t hash32(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x7feb352dU;
+  x ^= x >> 15;
+  x *= 0x846ca68bU;
+  x ^= x >> 16;
+  return x;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LogLikelihood (Mahout mahout-math LogLikelihood.java).  __dmul_rn/__dsub_rn keep
+// nvcc from contracting x*log(x) - ... into FMAs so the evaluation order matches the JVM's.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double xlogx(long long x) {
+  return x == 0 ? 0.0 : __dmul_rn((double)x, log((double)x));
+}
+__device__ __forceinline__ double entropy2(long long a, long long b, bool varargs) {
+  if (varargs) return __dsub_rn(xlogx(a + b), __dadd_rn(__dadd_rn(0.0, xlogx(a)), xlogx(b)));
+  return __dsub_rn(__dsub_rn(xlogx(a + b), xlogx(a)), xlogx(b));
+}
+__device__ __forceinline__ double entropy4(long long a, long long b, long long c, long long d, bool varargs) {
+  if (varargs) {
+    double r = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(0.0, xlogx(a)), xlogx(b)), xlogx(c)), xlogx(d));
+    return __dsub_rn(xlogx(a + b + c + d), r);
+  }
+  return __dsub_rn(__dsub_rn(__dsub_rn(__dsub_rn(xlogx(a + b + c + d), xlogx(a)), xlogx(b)), xlogx(c)), xlogx(d));
+}
+__device__ __forceinline__ double llr_cells(long long k11, long long k12, long long k21, long long k22, bool varargs) {
+  double row_e = entropy2(k11 + k12, k21 + k22, varargs);
+  double col_e = entropy2(k11 + k21, k12 + k22, varargs);
+  double mat_e = entropy4(k11, k12, k21, k22, varargs);
+  double s = __dadd_rn(row_e, col_e);
+  if (s < mat_e) return 0.0;  // round off error
+  return __dmul_rn(2.0, __dsub_rn(s, mat_e));
+}
+// fused form used by the row kernel: row entropy hoisted per row (bit-identical sub-expression)
+__device__ __forceinline__ double llr_hoisted(long long k11, long long ra, long long cb, long long n, double row_e,
+                                              bool varargs) {
+  long long k12 = ra - k11, k21 = cb - k11, k22 = n - ra - cb + k11;
+  double col_e = entropy2(cb, n - cb, varargs);
+  double mat_e = entropy4(k11, k12, k21, k22, varargs);
+  double s = __dadd_rn(row_e, col_e);
+  if (s < mat_e) return 0.0;
+  return __dmul_rn(2.0, __dsub_rn(s, mat_e));
+}
+
+__global__ void k_debug_llr(long long n, const long long *k11, const long long *k12, const long long *k21,
+                            const long long *k22, uint32_t flags, double *out) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = llr_cells(k11[i], k12[i], k21[i], k22[i], (flags & CCO_FLAG_ENTROPY_VARARGS) != 0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row-parallel passes over a CSR matrix: SG lanes cooperate on one user row.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSG = 8;  // lanes per user row in the preparation passes (avg row ~10-30 entries)
+
+// flags[0] |= malformed (row_ptr not monotone / column out of range), flags[1] |= not canonical
+__global__ void k_check_rows(long long n_rows, int32_t n_cols, const long long *__restrict__ rp,
+                             const int32_t *__restrict__ col, int *flags) {
+  const int lane = threadIdx.x % kSG;
+  long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / kSG;
+  const long long stride = (long long)gridDim.x * blockDim.x / kSG;
+  int bad = 0, unsorted = 0;
+  for (; row < n_rows; row += stride) {
+    long long s = rp[row], e = rp[row + 1];
+    if (e < s) { bad = 1; continue; }
+    for (long long q = s + lane; q < e; q += kSG) {
+      int32_t c = col[q];
+      if (c < 0 || c >= n_cols) bad = 1;
+      if (q > s && col[q - 1] >= c) unsorted = 1;
+    }
+  }
+  if (bad) atomicOr(&flags[0], 1);
+  if (unsorted) atomicOr(&flags[1], 1);
+}
+
+// raw column counts c_j of rows [row_begin,row_end) (numNonZeroElementsPerColumn of the raw matrix)
+__global__ void k_col_histogram(long long row_begin, long long row_end, const long long *__restrict__ rp,
+                                const int32_t *__restrict__ col, int32_t *__restrict__ counts) {
+  // element-parallel over the contiguous slice rp[row_begin]..rp[row_end]; warp-uniform trip count
+  const long long s = rp[row_begin], e = rp[row_end];
+  const int lane = threadIdx.x & 31;
+  for (long long q0 = s + blockIdx.x * (long long)blockDim.x + (threadIdx.x & ~31); q0 < e;
+       q0 += (long long)gridDim.x * blockDim.x) {
+    const long long q = q0 + lane;
+    const bool act = q < e;
+    const unsigned am = __ballot_sync(0xffffffffu, act);
+    if (act) {
+      int32_t c = col[q];
+      // warp-aggregate lanes hitting the same column (Zipf-hot columns)
+      unsigned peers = __match_any_sync(am, c);
+      if ((__ffs(peers) - 1) == lane) atomicAdd(&counts[c], __popc(peers));
+    }
+  }
+}
+
+__device__ __forceinline__ double sample_rate(long long d, double c, int32_t m, bool intdiv) {
+  double row_rate = 1.0;
+  if (d > 0) {
+    long long md = d < m ? d : (long long)m;
+    row_rate = intdiv ? (double)(md / d) : __ddiv_rn((double)md, (double)d);
+  }
+  double col_rate = __ddiv_rn(c < (double)m ? c : (double)m, c);
+  return row_rate < col_rate ? row_rate : col_rate;
+}
+
+// pass 1 of sampleDownAndBinarize: kept entries per row + post-sample column marginals
+__global__ void k_downsample_count(long long n_rows, const long long *__restrict__ rp, const int32_t *__restrict__ col,
+                                   const int32_t *__restrict__ raw_counts, int32_t m, int32_t seed, uint32_t flags,
+                                   uint32_t *__restrict__ kept_per_row, int32_t *__restrict__ new_counts) {
+  const int lane = threadIdx.x % kSG;
+  const unsigned sg_mask = ((1u << kSG) - 1u) << ((threadIdx.x & 31) / kSG * kSG);
+  long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / kSG;
+  const long long stride = (long long)gridDim.x * blockDim.x / kSG;
+  const bool intdiv = (flags & CCO_FLAG_ROWRATE_INTDIV) != 0;
+  // all lanes of a sub-group share `row`, so loop trip counts are sub-group uniform
+  for (; row < n_rows; row += stride) {
+    long long s = rp[row], e = rp[row + 1], d = e - s;
+    uint32_t kept = 0;
+    for (long long q0 = s; q0 < e; q0 += kSG) {
+      long long q = q0 + lane;
+      bool keep = false;
+      int32_t j = 0;
+      if (q < e) {
+        j = col[q];
+        double rate = sample_rate(d, (double)raw_counts[j], m, intdiv);
+        keep = sample_u01(seed, (uint32_t)row, (uint32_t)j) <= rate;
+      }
+      if (keep) atomicAdd(&new_counts[j], 1);
+      kept += __popc(__ballot_sync(sg_mask, keep) & sg_mask);
+    }
+    if (lane == 0) kept_per_row[row] = kept;
+  }
+}
+
+// pass 2: ordered compaction (ascending columns are preserved)
+__global__ void k_downsample_write(long long n_rows, const long long *__restrict__ rp, const int32_t *__restrict__ col,
+                                   const int32_t *__restrict__ raw_counts, int32_t m, int32_t seed, uint32_t flags,
+                                   const uint32_t *__restrict__ new_ptr, int32_t *__restrict__ new_col) {
+  const int lane = threadIdx.x % kSG;
+  const int sg_shift = (threadIdx.x & 31) / kSG * kSG;
+  const unsigned sg_mask = ((1u << kSG) - 1u) << sg_shift;
+  long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / kSG;
+  const long long stride = (long long)gridDim.x * blockDim.x / kSG;
+  const bool intdiv = (flags & CCO_FLAG_ROWRATE_INTDIV) != 0;
+  for (; row < n_rows; row += stride) {
+    long long s = rp[row], e = rp[row + 1], d = e - s;
+    uint32_t w = new_ptr[row];
+    for (long long q0 = s; q0 < e; q0 += kSG) {
+      long long q = q0 + lane;
+      bool keep = false;
+      int32_t j = 0;
+      if (q < e) {
+        j = col[q];
+        double rate = sample_rate(d, (double)raw_counts[j], m, intdiv);
+        keep = sample_u01(seed, (uint32_t)row, (uint32_t)j) <= rate;
+      }
+      unsigned b = (__ballot_sync(sg_mask, keep) & sg_mask) >> sg_shift;
+      if (keep) new_col[w + __popc(b & ((1u << lane) - 1u))] = j;
+      w += __popc(b);
+    }
+  }
+}
+
+// `drmA.t`: scatter users into per-item lists (order inside a list is irrelevant to the integer counts)
+__global__ void k_transpose_scatter(long long n_rows, const uint32_t *__restrict__ rp, const int32_t *__restrict__ col,
+                                    uint32_t *__restrict__ cursor, int32_t *__restrict__ users) {
+  const int lane = threadIdx.x % kSG;
+  long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / kSG;
+  const long long stride = (long long)gridDim.x * blockDim.x / kSG;
+  for (; row < n_rows; row += stride) {
+    uint32_t s = rp[row], e = rp[row + 1];
+    for (uint32_t q = s + lane; q < e; q += kSG) users[atomicAdd(&cursor[col[q]], 1u)] = (int32_t)row;
+  }
+}
+
+// w_a = sum over users of item a of degB'(u)  (= products of output row a), saturating; also P
+__global__ void k_row_work(int32_t n_items, const uint32_t *__restrict__ at_ptr, const int32_t *__restrict__ at_users,
+                           const uint32_t *__restrict__ b_ptr, uint32_t *__restrict__ row_work,
+                           unsigned long long *__restrict__ work64, int32_t *__restrict__ item_ids) {
+  const int lane = threadIdx.x % kSG;
+  const unsigned sg_mask = ((1u << kSG) - 1u) << ((threadIdx.x & 31) / kSG * kSG);
+  int item = (blockIdx.x * blockDim.x + threadIdx.x) / kSG;
+  const int stride = gridDim.x * blockDim.x / kSG;
+  for (; item < n_items; item += stride) {
+    uint32_t s = at_ptr[item], e = at_ptr[item + 1];
+    unsigned long long w = 0;
+    for (uint32_t q = s + lane; q < e; q += kSG) {
+      int32_t u = at_users[q];
+      w += b_ptr[u + 1] - b_ptr[u];
+    }
+#pragma unroll
+    for (int o = kSG / 2; o > 0; o >>= 1) w += __shfl_xor_sync(sg_mask, w, o);
+    if (lane == 0) {
+      row_work[item] = w > 0xffffffffULL ? 0xffffffffu : (uint32_t)w;
+      work64[item] = w;
+      item_ids[item] = item;
+    }
+  }
+}
+
+// bin boundaries inside the work-descending row list: bin b holds rows whose distinct-cell bound
+// D = min(w, n_cols_b) satisfies thresholds[b-1] >= D > thresholds[b]  (thresholds descending)
+__global__ void k_bin_bounds(int32_t n_rows, const uint32_t *__restrict__ sorted_work, int32_t n_bins,
+                             const uint32_t *__restrict__ thresholds, int32_t *__restrict__ bounds) {
+  int b = threadIdx.x;
+  if (b > n_bins) return;
+  if (b == 0) { bounds[0] = 0; return; }
+  // first index whose work <= thresholds[b-1]  (sorted descending)
+  uint32_t t = thresholds[b - 1];
+  int lo = 0, hi = n_rows;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (sorted_work[mid] > t) lo = mid + 1; else hi = mid;
+  }
+  bounds[b] = lo;
+}
+
+// ------------------------------------------------------------------------------------------------
+// The fused row kernel: one CTA per primary item a.
+//   count : for u in users(a): for b in B'[u]: table[b]++            (shared-memory accumulator)
+//   score : for every touched b: LLR(k11, colA[a], colB[b], N) in fp64, fused, in registers
+//   select: running top-k under the total order (llr desc, col asc)  (candidate buffer + prune)
+// DENSE: the table is indexed by b directly (n_cols_b <= slots); otherwise a packed open-addressing
+// hash (key << count_bits | count), multi-pass over hash partitions when the row's distinct-cell
+// bound exceeds the table capacity.
+// ------------------------------------------------------------------------------------------------
+struct Cand {
+  unsigned long long key;  // bit pattern of the (positive) fp64 LLR: monotone
+  uint32_t col;
+  uint32_t cnt;
+};
+
+__device__ __forceinline__ bool cand_better(unsigned long long ka, uint32_t ca, unsigned long long kb, uint32_t cb) {
+  return ka > kb || (ka == kb && ca < cb);
+}
+
+template <int THREADS>
+__device__ void sort_candidates(unsigned long long *ckey, uint32_t *ccol, uint32_t *ccnt, int n) {
+  // bitonic sort, best first; pads [n, n2) with key 0 (never a valid candidate: LLR > 0)
+  int n2 = 1;
+  while (n2 < n) n2 <<= 1;
+  for (int i = n + threadIdx.x; i < n2; i += THREADS) { ckey[i] = 0ULL; ccol[i] = 0xffffffffu; ccnt[i] = 0; }
+  __syncthreads();
+  for (int k2 = 2; k2 <= n2; k2 <<= 1) {
+    for (int j = k2 >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n2; i += THREADS) {
+        int p = i ^ j;
+        if (p > i) {
+          bool up = (i & k2) == 0;  // this sub-sequence sorted best-first
+          unsigned long long ki = ckey[i], kp = ckey[p];
+          uint32_t ci = ccol[i], cp = ccol[p];
+          bool swap = up ? cand_better(kp, cp, ki, ci) : cand_better(ki, ci, kp, cp);
+          if (swap) {
+            ckey[i] = kp; ckey[p] = ki;
+            ccol[i] = cp; ccol[p] = ci;
+            uint32_t t = ccnt[i]; ccnt[i] = ccnt[p]; ccnt[p] = t;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+template <int THREADS, bool DENSE>
+__global__ void __launch_bounds__(THREADS) k_rows(const RowArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // layout: ckey[cbuf] (8B) | ccol[cbuf] | ccnt[cbuf] | table[slots]
+  unsigned long long *ckey = reinterpret_cast<unsigned long long *>(smem_raw);
+  uint32_t *ccol = reinterpret_cast<uint32_t *>(ckey + a.cbuf);
+  uint32_t *ccnt = ccol + a.cbuf;
+  uint32_t *table = ccnt + a.cbuf;
+  __shared__ int s_ncand;
+  __shared__ unsigned long long s_thr_key;
+  __shared__ uint32_t s_thr_col;
+  __shared__ int s_have_thr;
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int row_begin = a.bin_bounds[a.bin], row_end = a.bin_bounds[a.bin + 1];
+  const bool varargs = (a.flags & CCO_FLAG_ENTROPY_VARARGS) != 0;
+  const int cbits = a.count_bits;
+  const uint32_t cmask = (cbits >= 32) ? 0xffffffffu : ((1u << cbits) - 1u);
+  const uint32_t slots = (uint32_t)a.slots;
+  const int prune_limit = a.cbuf - THREADS;
+  unsigned long long distinct_local = 0;
+
+  for (int ri = row_begin + blockIdx.x; ri < row_end; ri += gridDim.x) {
+    const int item = a.rows_sorted[ri];
+    const uint32_t u_begin = a.at_ptr[item], u_end = a.at_ptr[item + 1];
+    const long long ra = a.marg_a[item];
+    const double row_e = entropy2(ra, a.n_users - ra, varargs);
+    uint32_t n_pass = 1;
+    if (!DENSE) {
+      uint32_t w = a.row_work[item];
+      uint32_t dbound = w < (uint32_t)a.n_cols_b ? w : (uint32_t)a.n_cols_b;
+      n_pass = (dbound + (uint32_t)a.cap - 1u) / (uint32_t)a.cap;
+      if (n_pass == 0) n_pass = 1;
+    }
+    if (tid == 0) { s_ncand = 0; s_have_thr = 0; }
+    int emit_cursor_base = 0;
+
+    for (uint32_t pass = 0; pass < n_pass; ++pass) {
+      // ---- clear --------------------------------------------------------------------------------
+      for (uint32_t i = tid; i < slots; i += THREADS) table[i] = DENSE ? 0u : kEmpty;
+      __syncthreads();
+      // ---- count --------------------------------------------------------------------------------
+      {
+        constexpr int SG = 8;  // lanes per user
+        const int sg = tid / SG, sl = tid % SG;
+        for (uint32_t i = u_begin + sg; i < u_end; i += THREADS / SG) {
+          const int32_t u = a.at_users[i];
+          const uint32_t s = a.b_ptr[u], e = a.b_ptr[u + 1];
+          for (uint32_t q = s + sl; q < e; q += SG) {
+            const uint32_t b = (uint32_t)a.b_col[q];
+            if (DENSE) {
+              atomicAdd(&table[b], 1u);
+            } else {
+              const uint32_t h = hash32(b);
+              if (n_pass > 1 && (h % n_pass) != pass) continue;
+              uint32_t slot = __umulhi(h * 0x9e3779b1u, slots);
+              const uint32_t want = b << cbits;
+              uint32_t probes = 0;
+              while (true) {
+                uint32_t w = *reinterpret_cast<volatile uint32_t *>(&table[slot]);
+                if ((w >> cbits) == b && w != kEmpty) { atomicAdd(&table[slot], 1u); break; }
+                if (w == kEmpty) {
+                  uint32_t old = atomicCAS(&table[slot], kEmpty, want | 1u);
+                  if (old == kEmpty) break;
+                  if ((old >> cbits) == b) { atomicAdd(&table[slot], 1u); break; }
+                }
+                slot = (slot + 1 == slots) ? 0 : slot + 1;
+                if (++probes > slots) { atomicOr(a.err_flag, 1); break; }
+              }
+            }
+          }
+        }
+      }
+      __syncthreads();
+      // ---- score + select -------------------------------------------------------------------------
+      const uint32_t scan_n = DENSE ? (uint32_t)a.n_cols_b : slots;
+      for (uint32_t base = 0; base < scan_n; base += THREADS) {
+        const uint32_t slot = base + tid;
+        uint32_t b = 0, k11 = 0;
+        bool valid = false;
+        if (slot < scan_n) {
+          uint32_t w = table[slot];
+          if (DENSE) { valid = w != 0; b = slot; k11 = w; }
+          else { valid = w != kEmpty; b = w >> cbits; k11 = w & cmask; }
+        }
+        if (valid) ++distinct_local;
+        unsigned long long key = 0;
+        bool pass_ok = false;
+        if (a.emit_all) {
+          pass_ok = valid;
+        } else if (valid && !(a.self && (int)b == item)) {
+          const long long cb = a.marg_b[b];
+          double v = llr_hoisted((long long)k11, ra, cb, a.n_users, row_e, varargs);
+          pass_ok = v > 0.0 && (!a.has_min_llr || v >= a.min_llr);
+          key = (unsigned long long)__double_as_longlong(v);
+          if (pass_ok && s_have_thr) pass_ok = cand_better(key, b, s_thr_key, s_thr_col);
+        }
+        // warp-aggregated append
+        unsigned m = __ballot_sync(0xffffffffu, pass_ok);
+        if (m) {
+          int basepos = 0;
+          if (lane == 0) basepos = atomicAdd(&s_ncand, __popc(m));
+          basepos = __shfl_sync(0xffffffffu, basepos, 0);
+          if (pass_ok) {
+            int pos = basepos + __popc(m & ((1u << lane) - 1u));
+            if (a.emit_all) {
+              size_t o = (size_t)item * a.out_stride + emit_cursor_base + pos;
+              a.out_col[o] = (int32_t)b;
+              a.out_cnt[o] = (int32_t)k11;
+            } else {
+              ckey[pos] = key; ccol[pos] = b; ccnt[pos] = k11;
+            }
+          }
+        }
+        __syncthreads();
+        if (!a.emit_all) {
+          int n = s_ncand;
+          if (n > prune_limit) {
+            sort_candidates<THREADS>(ckey, ccol, ccnt, n);
+            if (tid == 0) {
+              int keep = n < a.top_k ? n : a.top_k;
+              s_ncand = keep;
+              if (n >= a.top_k) { s_thr_key = ckey[a.top_k - 1]; s_thr_col = ccol[a.top_k - 1]; s_have_thr = 1; }
+            }
+            __syncthreads();
+          }
+        }
+      }
+      if (a.emit_all) {
+        __syncthreads();
+        emit_cursor_base += s_ncand;
+        __syncthreads();
+        if (tid == 0) s_ncand = 0;
+      }
+      __syncthreads();
+    }
+    // ---- final select + write -------------------------------------------------------------------
+    if (a.emit_all) {
+      if (tid == 0) a.out_len[item] = emit_cursor_base;
+    } else {
+      int n = s_ncand;
+      if (n > 0) {
+        sort_candidates<THREADS>(ckey, ccol, ccnt, n);
+        int keep = n < a.top_k ? n : a.top_k;
+        for (int i = tid; i < keep; i += THREADS) {
+          size_t o = (size_t)item * a.out_stride + i;
+          a.out_col[o] = (int32_t)ccol[i];
+          a.out_llr[o] = __longlong_as_double((long long)ckey[i]);
+          a.out_cnt[o] = (int32_t)ccnt[i];
+        }
+        if (tid == 0) a.out_len[item] = keep;
+      } else if (tid == 0) {
+        a.out_len[item] = 0;
+      }
+    }
+    __syncthreads();
+  }
+  // stats: distinct cells visited by this CTA
+  for (int o = 16; o > 0; o >>= 1) distinct_local += __shfl_xor_sync(0xffffffffu, distinct_local, o);
+  if (lane == 0 && distinct_local) atomicAdd(a.stat_distinct, distinct_local);
+}
+
+// packed output: gather the strided per-row results into CSR order
+__global__ void k_compact_rows(int32_t row_lo, int32_t n_rows, int32_t stride, const long long *__restrict__ out_ptr,
+                               const int32_t *__restrict__ len, const int32_t *__restrict__ col,
+                               const double *__restrict__ llr, const int32_t *__restrict__ cnt,
+                               int32_t *__restrict__ p_col, double *__restrict__ p_llr, int32_t *__restrict__ p_cnt) {
+  // one warp per row
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = warp; r < n_rows; r += nwarps) {
+    int item = row_lo + r;
+    int n = len[item];
+    long long o = out_ptr[r];
+    size_t src = (size_t)item * stride;
+    for (int i = lane; i < n; i += 32) {
+      p_col[o + i] = col[src + i];
+      if (p_llr) p_llr[o + i] = llr[src + i];
+      p_cnt[o + i] = cnt[src + i];
+    }
+  }
+}
+
+// ---- canonicalisation slow path (unsorted / duplicated input rows) -------------------------------
+__global__ void k_expand_keys(long long n_rows, const long long *__restrict__ rp, const int32_t *__restrict__ col,
+                              unsigned long long *__restrict__ keys) {
+  const int lane = threadIdx.x % kSG;
+  long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / kSG;
+  const long long stride = (long long)gridDim.x * blockDim.x / kSG;
+  for (; row < n_rows; row += stride) {
+    long long s = rp[row], e = rp[row + 1];
+    for (long long q = s + lane; q < e; q += kSG) keys[q] = ((unsigned long long)row << 32) | (uint32_t)col[q];
+  }
+}
+__global__ void k_unique_flags(long long n, const unsigned long long *__restrict__ keys, uint32_t *__restrict__ flag) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    flag[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+}
+__global__ void k_unique_scatter(long long n, const unsigned long long *__restrict__ keys,
+                                 const uint32_t *__restrict__ flag, const uint32_t *__restrict__ pos,
+                                 unsigned long long *__restrict__ out_keys, int32_t *__restrict__ out_col) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    if (flag[i]) { out_keys[pos[i]] = keys[i]; out_col[pos[i]] = (int32_t)(keys[i] & 0xffffffffULL); }
+}
+// row_ptr[r] = first index whose key >= (r << 32)
+__global__ void k_rowptr_from_keys(long long n_rows, long long n_unique, const unsigned long long *__restrict__ keys,
+                                   long long *__restrict__ rp) {
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r <= n_rows; r += (long long)gridDim.x * blockDim.x) {
+    unsigned long long t = (unsigned long long)r << 32;
+    long long lo = 0, hi = n_unique;
+    while (lo < hi) {
+      long long mid = (lo + hi) >> 1;
+      if (keys[mid] < t) lo = mid + 1; else hi = mid;
+    }
+    rp[r] = lo;
+  }
+}
+
+__global__ void k_max_i32(long long n, const int32_t *__restrict__ x, int32_t *__restrict__ out) {
+  int32_t m = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    m = max(m, x[i]);
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
+__global__ void k_len_to_i64(int32_t row_lo, int32_t n, const int32_t *__restrict__ len, long long *__restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = len[row_lo + i];
+}
+
+}  // namespace cco

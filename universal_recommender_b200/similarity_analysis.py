@@ -1,0 +1,245 @@
+"""Python mirror of org.apache.mahout.math.cf.SimilarityAnalysis as the reference calls it
+(/root/reference/src/main/scala/URAlgorithm.scala:323-329, 343-346), running on the B200 through the
+C ABI of include/cco_b200.h.  Same names, argument meaning and error behaviour; the arithmetic is
+the hand-written sm_100a path in csrc/ -- there is no CPU implementation in this package."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _native as N
+from .indexed_dataset import IndexedDataset
+
+
+@dataclass
+class DownsamplableCrossOccurrenceDataset:
+    """org.apache.mahout.math.cf.DownsamplableCrossOccurrenceDataset as constructed at
+    URAlgorithm.scala:336-340 (defaults 500 / 50 / None)."""
+    iD: IndexedDataset
+    maxElementsPerRow: int = 500
+    maxInterestingElements: int = 50
+    minLLROpt: Optional[float] = None
+    parOpts: object = None   # Spark partitioning hints: meaningless here, accepted and ignored
+
+
+@dataclass
+class TrainStats:
+    n_users: int
+    nnz_in_total: int
+    nnz_downsampled: list
+    products: list
+    distinct_cells: list
+    out_nnz: list
+    ms_h2d: float
+    ms_prepare: float
+    ms_cooccurrence: float
+    ms_total: float
+    ms_indicator: list
+    n_kernel_launches: int
+
+
+class CcoContext:
+    """One GPU context (= cco_ctx_t).  One process per GPU; for world_size > 1 pass the 128-byte NCCL id
+    from `CcoContext.nccl_unique_id()` of rank 0 (distribute it with any host transport)."""
+
+    def __init__(self, device: int = 0, rank: int = 0, world_size: int = 1, nccl_unique_id: bytes | None = None):
+        L = N.lib()
+        self._L = L
+        self._uid = None
+        cfg = N.ConfigT(device, rank, world_size, 0, None)
+        if world_size > 1:
+            if nccl_unique_id is None or len(nccl_unique_id) != 128:
+                raise N.CcoInvalidArgument(N.E_INVALID_ARG, "world_size > 1 needs the 128-byte nccl_unique_id")
+            self._uid = (C.c_ubyte * 128).from_buffer_copy(nccl_unique_id)
+            cfg.nccl_unique_id = C.cast(self._uid, C.POINTER(C.c_ubyte))
+        h = C.c_void_p()
+        N.check(L.cco_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+        self.rank, self.world_size, self.device = rank, world_size, device
+        self.last_stats: TrainStats | None = None
+
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        buf = (C.c_ubyte * 128)()
+        N.check(N.lib().cco_nccl_unique_id(buf))
+        return bytes(buf)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.cco_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- pinned host buffers (what the JNI shim wraps as direct ByteBuffers) -------------------------
+    def host_array(self, n: int, dtype) -> np.ndarray:
+        dt = np.dtype(dtype)
+        p = C.c_void_p()
+        N.check(self._L.cco_host_alloc(self._h, max(n, 1) * dt.itemsize, C.byref(p)))
+        buf = (C.c_byte * (max(n, 1) * dt.itemsize)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dt, count=n)
+        arr._cco_pinned = p  # keep the address for host_free
+        return arr
+
+    def host_free(self, arr: np.ndarray):
+        base = arr
+        while getattr(base, "_cco_pinned", None) is None and base.base is not None:
+            base = base.base
+        p = getattr(base, "_cco_pinned", None)
+        if p is not None:
+            self._L.cco_host_free(self._h, p)
+
+    # ---- the hot path ---------------------------------------------------------------------------------------
+    def train_csr(self, mats: Sequence[tuple[int, int, np.ndarray, np.ndarray]], params: Sequence[tuple[int, int, Optional[float]]],
+                  seed: int, flags: int = 0):
+        """Raw entry: mats = [(n_rows, n_cols, row_ptr int64, col_idx int32)], params = [(m, k, minLLR|None)].
+        -> list of (row_begin, row_end, n_cols, row_ptr, col_idx, llr, count) numpy copies, one per matrix."""
+        L = self._L
+        n = len(mats)
+        keep = []
+        cm = (N.CsrT * n)()
+        for i, (nr, nc, rp, ci) in enumerate(mats):
+            rp = np.ascontiguousarray(rp, dtype=np.int64)
+            ci = np.ascontiguousarray(ci, dtype=np.int32)
+            keep.append((rp, ci))
+            cm[i] = N.as_csr_t(nr, nc, rp, ci)
+        cp = (N.ParamsT * n)(*[N.ParamsT(int(m), int(k), 0 if ml is None else 1, 0.0 if ml is None else float(ml))
+                               for (m, k, ml) in params])
+        res = C.c_void_p()
+        N.check(L.cco_train(self._h, n, cm, cp, C.c_int32(_to_i32(seed)), flags, C.byref(res)))
+        try:
+            out = []
+            for i in range(n):
+                rb, re_ = C.c_int64(), C.c_int64()
+                N.check(L.cco_result_row_range(res, i, C.byref(rb), C.byref(re_)))
+                nr, nc = C.c_int64(), C.c_int32()
+                prp, pci, pll, pcn = C.POINTER(C.c_int64)(), C.POINTER(C.c_int32)(), C.POINTER(C.c_double)(), C.POINTER(C.c_int32)()
+                N.check(L.cco_result_matrix(res, i, C.byref(nr), C.byref(nc), C.byref(prp), C.byref(pci), C.byref(pll), C.byref(pcn)))
+                rp = np.ctypeslib.as_array(prp, shape=(nr.value + 1,)).copy()
+                nnz = int(rp[-1])
+                if nnz:
+                    ci = np.ctypeslib.as_array(pci, shape=(nnz,)).copy()
+                    ll = np.ctypeslib.as_array(pll, shape=(nnz,)).copy()
+                    cn = np.ctypeslib.as_array(pcn, shape=(nnz,)).copy()
+                else:
+                    ci, ll, cn = np.zeros(0, np.int32), np.zeros(0, np.float64), np.zeros(0, np.int32)
+                out.append((rb.value, re_.value, nc.value, rp, ci, ll, cn))
+            st = N.StatsT()
+            N.check(L.cco_result_stats(res, C.byref(st)))
+            self.last_stats = TrainStats(st.n_users, st.nnz_in_total, list(st.nnz_downsampled)[:n], list(st.products)[:n],
+                                         list(st.distinct_cells)[:n], list(st.out_nnz)[:n], st.ms_h2d, st.ms_prepare,
+                                         st.ms_cooccurrence, st.ms_total, list(st.ms_indicator)[:n], st.n_kernel_launches)
+            return out
+        finally:
+            L.cco_result_free(res)
+
+    # ---- debug / parity entries ---------------------------------------------------------------------------
+    def debug_llr(self, k11, k12, k21, k22, flags: int = 0) -> np.ndarray:
+        a = [np.ascontiguousarray(x, dtype=np.int64) for x in (k11, k12, k21, k22)]
+        out = np.zeros(len(a[0]), dtype=np.float64)
+        p = C.POINTER(C.c_int64)
+        N.check(self._L.cco_debug_llr(self._h, len(out), *[x.ctypes.data_as(p) for x in a], flags,
+                                      out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def debug_downsample(self, n_rows, n_cols, row_ptr, col_idx, max_interactions: int, seed: int, flags: int = 0):
+        rp = np.ascontiguousarray(row_ptr, dtype=np.int64)
+        ci = np.ascontiguousarray(col_idx, dtype=np.int32)
+        m = N.as_csr_t(n_rows, n_cols, rp, ci)
+        orp, oci = C.POINTER(C.c_int64)(), C.POINTER(C.c_int32)()
+        raw = np.zeros(max(n_cols, 1), np.int32)
+        new = np.zeros(max(n_cols, 1), np.int32)
+        N.check(self._L.cco_debug_downsample(self._h, C.byref(m), max_interactions, _to_i32(seed), flags, C.byref(orp),
+                                             C.byref(oci), raw.ctypes.data_as(C.POINTER(C.c_int32)),
+                                             new.ctypes.data_as(C.POINTER(C.c_int32))))
+        r = np.ctypeslib.as_array(orp, shape=(n_rows + 1,)).copy()
+        nnz = int(r[-1])
+        c = np.ctypeslib.as_array(oci, shape=(nnz,)).copy() if nnz else np.zeros(0, np.int32)
+        self._L.cco_free(orp)
+        self._L.cco_free(oci)
+        return r, c, raw[:n_cols], new[:n_cols]
+
+    def debug_cooccurrence(self, a, b):
+        """a, b = (n_rows, n_cols, row_ptr, col_idx) canonical binary matrices -> (row_ptr, col_idx, count) of A^T B."""
+        keep = []
+        cs = []
+        for (nr, nc, rp, ci) in (a, b):
+            rp = np.ascontiguousarray(rp, dtype=np.int64)
+            ci = np.ascontiguousarray(ci, dtype=np.int32)
+            keep.append((rp, ci))
+            cs.append(N.as_csr_t(nr, nc, rp, ci))
+        orp, oci, ocn = C.POINTER(C.c_int64)(), C.POINTER(C.c_int32)(), C.POINTER(C.c_int32)()
+        N.check(self._L.cco_debug_cooccurrence(self._h, C.byref(cs[0]), C.byref(cs[1]), C.byref(orp), C.byref(oci), C.byref(ocn)))
+        r = np.ctypeslib.as_array(orp, shape=(a[1] + 1,)).copy()
+        nnz = int(r[-1])
+        c = np.ctypeslib.as_array(oci, shape=(nnz,)).copy() if nnz else np.zeros(0, np.int32)
+        n = np.ctypeslib.as_array(ocn, shape=(nnz,)).copy() if nnz else np.zeros(0, np.int32)
+        for p in (orp, oci, ocn):
+            self._L.cco_free(p)
+        return r, c, n
+
+
+def _to_i32(seed: int) -> int:
+    """`.toInt` of a Long seed as in URAlgorithm.scala:325,345 (wraps)."""
+    s = int(seed) & 0xffffffff
+    return s - (1 << 32) if s & 0x80000000 else s
+
+
+_default_ctx: CcoContext | None = None
+
+
+def default_context() -> CcoContext:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = CcoContext(device=int(os.environ.get("LOCAL_RANK", "0")) if os.environ.get("CCO_USE_LOCAL_RANK") else 0)
+    return _default_ctx
+
+
+class SimilarityAnalysis:
+    """Drop-in for the two static calls of URAlgorithm.calcAll."""
+
+    @staticmethod
+    def crossOccurrenceDownsampled(datasets: Sequence[DownsamplableCrossOccurrenceDataset], randomSeed: int = 0xdeadbeef,
+                                   ctx: CcoContext | None = None, flags: int = 0) -> list[IndexedDataset]:
+        """URAlgorithm.scala:343-346.  datasets[0] is the primary (A).  Returns one IndexedDataset per input,
+        rowIDs = A.columnIDs, columnIDs = B_i.columnIDs, values = LLR, rows sorted (llr desc, col asc)."""
+        if len(datasets) == 0:
+            raise N.CcoInvalidArgument(N.E_INVALID_ARG, "datasets is empty")
+        ctx = ctx or default_context()
+        a = datasets[0].iD
+        mats = [(d.iD.n_rows, d.iD.n_cols, d.iD.row_ptr, d.iD.col_idx) for d in datasets]
+        params = [(d.maxElementsPerRow, d.maxInterestingElements, d.minLLROpt) for d in datasets]
+        res = ctx.train_csr(mats, params, randomSeed, flags)
+        out = []
+        for d, (rb, re_, nc, rp, ci, ll, cn) in zip(datasets, res):
+            if ctx.world_size == 1:
+                out.append(a.create(rp, ci, a.column_ids, d.iD.column_ids, ll, cn))
+            else:   # this rank's row slice, padded to the full primary-item row space
+                full = np.zeros(a.n_cols + 1, dtype=np.int64)
+                full[rb + 1:re_ + 1] = rp[1:]
+                full[re_ + 1:] = rp[-1]
+                out.append(a.create(full, ci, a.column_ids, d.iD.column_ids, ll, cn))
+        return out
+
+    @staticmethod
+    def cooccurrencesIDSs(indexedDatasets: Sequence[IndexedDataset], randomSeed: int = 0xdeadbeef,
+                          maxInterestingItemsPerThing: int = 50, maxNumInteractions: int = 500,
+                          ctx: CcoContext | None = None, flags: int = 0) -> list[IndexedDataset]:
+        """URAlgorithm.scala:323-329: one global (k, m) for every matrix."""
+        ds = [DownsamplableCrossOccurrenceDataset(i, maxNumInteractions, maxInterestingItemsPerThing, None)
+              for i in indexedDatasets]
+        return SimilarityAnalysis.crossOccurrenceDownsampled(ds, randomSeed, ctx, flags)
