@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py -- CCO train events/sec to indicator model (BASELINE.json metric) on N B200s.
+
+A "step" is one complete pass of the hot path (downsample -> A'^T A' / A'^T B'_i co-occurrence -> LLR -> top-k)
+over the whole synthetic workload.  Default workload: BASELINE.json configs[2] ("C3": 1M users x 100K items,
+50M events, 1 primary + 3 secondary event types, k=50), the configuration the 1/2/4/8-GPU metric is quoted on
+and which fits one GPU.  `--workload C2` runs configs[1].
+
+  value    : events/s with the input matrices already resident in HBM (cco_dataset_upload outside the timed
+             region; results left packed in HBM), timed with CUDA events on the library's launch stream.
+  e2e      : events/s through the public C-ABI call cco_train with HOST (pinned) buffers: H2D of every matrix,
+             compute, D2H of every indicator inside the timed region.
+  roofline : algorithmic bytes of the fused A'^T B' row kernel (SURVEY.md 8d formula) / its CUDA-event time.
+  cpu_baseline : the oracle (CPU restatement of Mahout's algorithm, OpenMP) on a bounded sample, rank 0, N=1.
+
+`--impl reference` times the reference's own CPU implementation of the path.  The reference's implementation is
+Apache Mahout 0.13.0 on Spark (JVM), which is neither in /root/reference nor runnable in this image, so that arm
+runs the oracle port on all host cores (kind "port").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+import synth  # noqa: E402
+
+METRIC = "CCO train events/sec to indicator model"
+UNIT = "events/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("CCO_BENCH_WORKLOAD", "C3"))
+    ap.add_argument("--cpu-sample", default="auto", help="oracle sample: 'full', 'none' or a user fraction like 0.1")
+    ap.add_argument("--seed", type=int, default=42)
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.rows, self.p = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        sm, smax, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax = float(r[2])
+                for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                    if r[col].lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def algorithmic_bytes(st, i: int, n_items_a: int) -> float:
+    """bytes_alg(A,B) = 4 nnz(A') + 8 (I_A+1) + 8 nnz(A') + 4 P + 4 nnz(C) + 4 I_A + 12 out_nnz."""
+    nnz_a = st.nnz_downsampled[0]
+    return (4.0 * nnz_a + 8.0 * (n_items_a + 1) + 8.0 * nnz_a + 4.0 * st.products[i] + 4.0 * st.distinct_cells[i]
+            + 4.0 * n_items_a + 12.0 * st.out_nnz[i])
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------------------------------------
+def cpu_arm(w: synth.Workload, args, sample: str):
+    """Time the oracle (OpenMP, all host threads) on `sample` of the workload -> (events/s, cores, description, secs)."""
+    from oracle import oracle as orc
+    orc.build()
+    threads = orc.lib().orc_max_threads()
+    if sample == "full":
+        sw, desc = w, f"full {w.name} workload"
+    else:
+        f = float(sample)
+        sw = synth.make(w.name, n_users=max(int(synth.CONFIGS[w.name]["n_users"] * f), 1),
+                        n_events=max(int(synth.CONFIGS[w.name]["n_events"] * f), w.n_types))
+        desc = (f"{w.name} generator at {f:g} of the users and events ({sw.n_users} users x {sw.n_items} items, "
+                f"{sw.n_events} events, {sw.n_types} types), same item space/k/m")
+    mats = [orc.Csr(*m) for m in sw.mats]
+    prm = [orc.Params(*p) for p in sw.params]
+    t0 = time.perf_counter()
+    orc.train(mats, prm, args.seed, 0, threads)
+    dt = time.perf_counter() - t0
+    return sw.n_events / dt, threads, desc, dt, sw
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w_cfg = synth.CONFIGS[args.workload]
+    sample = "0.1" if args.cpu_sample == "auto" else args.cpu_sample
+    if sample == "none":
+        sample = "0.1"
+    # build the sample once, time W + K oracle runs on it
+    from oracle import oracle as orc
+    orc.build()
+    threads = orc.lib().orc_max_threads()
+    if sample == "full":
+        sw = synth.make(args.workload)
+        desc = f"full {args.workload} workload"
+    else:
+        f = float(sample)
+        sw = synth.make(args.workload, n_users=max(int(w_cfg["n_users"] * f), 1), n_events=max(int(w_cfg["n_events"] * f), 1))
+        desc = (f"{args.workload} generator at {f:g} of the users and events ({sw.n_users} users x {sw.n_items} items, "
+                f"{sw.n_events} events, {sw.n_types} types), same item space/k/m")
+    mats = [orc.Csr(*m) for m in sw.mats]
+    prm = [orc.Params(*p) for p in sw.params]
+    for _ in range(args.warmup):
+        orc.train(mats, prm, args.seed, 0, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.train(mats, prm, args.seed, 0, threads)
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    v = sw.n_events / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "int32 counts + f64 LLR", "data": "synthetic",
+            "config": {"workload": workload_desc(args.workload), "sample": desc},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc,
+                             "note": "CPU restatement of Mahout 0.13.0 SimilarityAnalysis (oracle/cco_oracle.c, OpenMP); the "
+                                     "reference's own Mahout-on-Spark path needs a JVM and is not runnable in this image"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_desc(name: str) -> str:
+    c = synth.CONFIGS[name]
+    return (f"{name}: synthetic Zipf (items s=1.0, users s=0.5), {c['n_users']} users x {c['n_items']} items, {c['n_events']} events, "
+            f"1 primary + {c['n_types'] - 1} secondary event types, maxCorrelatorsPerItem=50, maxItemsPerUser=500")
+
+
+# ---------------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+    import torch.distributed as dist
+
+    import universal_recommender_b200 as ur
+    from universal_recommender_b200 import _native as N
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this framework has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    uid = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        box = [ur.CcoContext.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        uid = box[0]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    t_gen = time.perf_counter()
+    w = synth.make(args.workload)
+    t_gen = time.perf_counter() - t_gen
+    n_items_a = w.mats[0][1]
+    ctx = ur.CcoContext(device=local_rank, rank=rank, world_size=world, nccl_unique_id=uid)
+
+    # inputs in pinned host memory (what the JNI shim's direct ByteBuffers would be)
+    pinned = []
+    for (nr, nc, rp, ci) in w.mats:
+        prp = ctx.host_array(len(rp), np.int64)
+        pci = ctx.host_array(len(ci), np.int32)
+        prp[:] = rp
+        pci[:] = ci
+        pinned.append((nr, nc, prp, pci))
+    h2d_bytes = sum(m[2].nbytes + m[3].nbytes for m in pinned)
+    flags = ur.FLAG_ASSUME_CANONICAL
+
+    # ---- device-resident throughput ------------------------------------------------------------------------
+    ds = ctx.upload(pinned, flags)
+    for _ in range(args.warmup):
+        ctx.train_dataset(ds, w.params, args.seed, flags | N.FLAG_RESULT_ON_DEVICE, copy_arrays=False)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ctx.timer_start()
+    rows_ms, launches = 0.0, 0
+    alg_bytes = 0.0
+    for _ in range(args.steps):
+        ctx.train_dataset(ds, w.params, args.seed, flags | N.FLAG_RESULT_ON_DEVICE, copy_arrays=False)
+        st = ctx.last_stats
+        rows_ms += sum(st.ms_indicator)
+        launches += st.n_kernel_launches
+        alg_bytes += sum(algorithmic_bytes(st, i, n_items_a) for i in range(w.n_types))
+    ms_dev = ctx.timer_stop()
+    barrier()
+    clocks = sampler.stop()
+    ms_dev = max_over_ranks(ms_dev)
+    ms_per_step = ms_dev / args.steps
+    value = w.n_events / (ms_per_step * 1e-3)
+    st_last = ctx.last_stats
+    ctx.free_dataset(ds)
+
+    # ---- end to end through cco_train with host buffers ------------------------------------------------------
+    for _ in range(args.warmup):
+        ctx.train_csr(pinned, w.params, args.seed, flags, copy_arrays=False)
+    barrier()
+    ctx.timer_start()
+    t0 = time.perf_counter()
+    d2h_bytes = 0
+    for _ in range(args.steps):
+        res = ctx.train_csr(pinned, w.params, args.seed, flags, copy_arrays=False)
+        d2h_bytes = sum(r[3].nbytes + int(r[3][-1]) * 16 for r in res)
+    ms_e2e = ctx.timer_stop()
+    wall_e2e = (time.perf_counter() - t0) * 1e3
+    barrier()
+    ms_e2e = max_over_ranks(max(ms_e2e, wall_e2e)) / args.steps
+    e2e_value = w.n_events / (ms_e2e * 1e-3)
+
+    # ---- roofline of the fused A'^T B' row kernel (all ranks' rows together) -----------------------------------
+    peak, peak_src = measured_peaks()
+    alg_total = sum_over_ranks(alg_bytes)
+    rows_ms_max = max_over_ranks(rows_ms)
+    achieved = alg_total / (rows_ms_max * 1e-3) / 1e9 / max(world, 1) if rows_ms_max > 0 else 0.0
+    n_row_launches = 4 * w.n_types * args.steps
+    roofline = {"bound": "hbm", "kernel": "k_rows (fused A'^T B' count + LLR + top-k; 4 work bins per indicator)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                "traffic": None, "algorithmic_bytes_per_launch": alg_total / max(world, 1) / n_row_launches,
+                "avg_launch_ms": rows_ms_max / n_row_launches,
+                "note": "per GPU; achieved = SURVEY 8(d) algorithmic bytes of this rank's rows / CUDA-event time of its row-kernel launches"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "int32 counts + f64 LLR", "data": "synthetic",
+            "config": {"workload": workload_desc(args.workload), "parallelism": f"item-row sharding x{world}",
+                       "l2": "inputs (%.0f MB) larger than the 126 MB L2; no explicit flush" % (h2d_bytes / 1e6)
+                       if h2d_bytes > 126e6 else "inputs fit L2 (%.0f MB); no explicit flush" % (h2d_bytes / 1e6),
+                       "resident": "value: matrices resident in HBM, indicators left packed in HBM",
+                       "products_per_step": int(sum_over_ranks(float(sum(st_last.products)))),
+                       "distinct_cells_per_step": int(sum_over_ranks(float(sum(st_last.distinct_cells)))),
+                       "datagen_s": round(t_gen, 1)},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
+                    "ms_per_step": ms_e2e},
+            "gpu_launches": int(launches),
+            "roofline": roofline}
+    if rank == 0 and world == 1 and args.cpu_sample != "none":
+        sample = "0.1" if args.cpu_sample == "auto" else args.cpu_sample
+        v, cores, desc, secs, _ = cpu_arm(w, args, sample)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc, "seconds": round(secs, 2)}
+    else:
+        line["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -77,7 +77,10 @@ enum {
    * 2 = varargs form xLogX(sum) - (sum of xLogX).  Last-bit difference only. */
   CCO_FLAG_ENTROPY_VARARGS = 2,
   /* inputs are already canonical (columns strictly ascending inside each row): skip the check */
-  CCO_FLAG_ASSUME_CANONICAL = 4
+  CCO_FLAG_ASSUME_CANONICAL = 4,
+  /* measurement only: leave the packed indicator arrays in HBM (col/llr/count host arrays are not
+   * filled; row_ptr is).  Used for the device-resident throughput number of bench.py. */
+  CCO_FLAG_RESULT_ON_DEVICE = 8
 };
 
 /*
@@ -103,6 +106,7 @@ typedef struct {
 
 typedef struct cco_ctx cco_ctx_t;
 typedef struct cco_result cco_result_t;
+typedef struct cco_dataset cco_dataset_t;
 
 /* Per-call statistics (the metrics/logging hook; replaces the logger.info dimension lines of
  * Preparator.scala:60,66,74 and feeds bench.py's roofline arithmetic). */
@@ -147,6 +151,21 @@ int cco_host_free(cco_ctx_t *ctx, void *p);
  */
 int cco_train(cco_ctx_t *ctx, int32_t n_mats, const cco_csr_t *mats, const cco_indicator_params_t *params,
               int32_t seed, uint32_t flags, cco_result_t **out);
+
+/*
+ * Split form of cco_train for callers that keep the matrices resident in HBM across trains
+ * (the `drmA.checkpoint()` / cache() role in Mahout): upload once (host->device copy, validation,
+ * canonicalisation), train any number of times with different parameters / seeds.
+ * cco_train(...) == cco_dataset_upload + cco_train_dataset + cco_dataset_free.
+ */
+int cco_dataset_upload(cco_ctx_t *ctx, int32_t n_mats, const cco_csr_t *mats, uint32_t flags, cco_dataset_t **out);
+int cco_train_dataset(cco_ctx_t *ctx, const cco_dataset_t *ds, const cco_indicator_params_t *params, int32_t seed,
+                      uint32_t flags, cco_result_t **out);
+int cco_dataset_free(cco_dataset_t *ds);
+
+/* CUDA-event stopwatch on the context's launch stream (what bench.py brackets its timed region with) */
+int cco_timer_start(cco_ctx_t *ctx);
+int cco_timer_stop(cco_ctx_t *ctx, float *ms);
 
 /* SimilarityAnalysis.cooccurrencesIDSs convenience: one global (k, m) for every matrix */
 int cco_cooccurrences_idss(cco_ctx_t *ctx, int32_t n_mats, const cco_csr_t *mats, int32_t seed,

@@ -10,7 +10,7 @@ name = sys.argv[1] if len(sys.argv) > 1 else "tiny"
 do_oracle = (len(sys.argv) <= 2) or sys.argv[2] != "nooracle"
 t0 = time.time(); w = synth.make(name); print(f"{name}: generated in {time.time()-t0:.1f}s; nnz per type {[int(m[2][-1]) for m in w.mats]}")
 ctx = ur.CcoContext()
-for it in range(3):
+for it in range(int(os.environ.get("QC_ITERS", "3"))):
     t0 = time.time(); res = ctx.train_csr(w.mats, w.params, seed=42, flags=ur.FLAG_ASSUME_CANONICAL); dt = time.time() - t0
     st = ctx.last_stats
     print(f"gpu iter {it}: wall {dt*1e3:.1f} ms  total {st.ms_total:.2f} h2d {st.ms_h2d:.2f} prep {st.ms_prepare:.2f} cooc {st.ms_cooccurrence:.2f} rows {['%.3f'%x for x in st.ms_indicator]} launches {st.n_kernel_launches}")

@@ -15,6 +15,7 @@ E_INVALID_ARG, E_CUDA, E_NCCL, E_OOM, E_SHAPE_MISMATCH, E_UNSUPPORTED = -1, -2, 
 FLAG_ROWRATE_INTDIV = 1
 FLAG_ENTROPY_VARARGS = 2
 FLAG_ASSUME_CANONICAL = 4
+FLAG_RESULT_ON_DEVICE = 8
 MAX_TOP_K = 2048
 
 
@@ -58,6 +59,7 @@ class StatsT(C.Structure):
 EXPORTS = [
     "cco_abi_version", "cco_last_error", "cco_status_string", "cco_device_count", "cco_nccl_unique_id",
     "cco_create", "cco_destroy", "cco_host_alloc", "cco_host_free", "cco_train", "cco_cooccurrences_idss",
+    "cco_dataset_upload", "cco_train_dataset", "cco_dataset_free", "cco_timer_start", "cco_timer_stop",
     "cco_result_num_matrices", "cco_result_row_range", "cco_result_matrix", "cco_result_stats", "cco_result_free",
     "cco_debug_cooccurrence", "cco_debug_downsample", "cco_debug_llr", "cco_free",
 ]
@@ -88,6 +90,11 @@ def lib():
     L.cco_train.argtypes = [C.c_void_p, C.c_int32, p(CsrT), p(ParamsT), C.c_int32, C.c_uint32, p(C.c_void_p)]
     L.cco_cooccurrences_idss.argtypes = [C.c_void_p, C.c_int32, p(CsrT), C.c_int32, C.c_int32, C.c_int32, C.c_uint32,
                                          p(C.c_void_p)]
+    L.cco_dataset_upload.argtypes = [C.c_void_p, C.c_int32, p(CsrT), C.c_uint32, p(C.c_void_p)]
+    L.cco_train_dataset.argtypes = [C.c_void_p, C.c_void_p, p(ParamsT), C.c_int32, C.c_uint32, p(C.c_void_p)]
+    L.cco_dataset_free.argtypes = [C.c_void_p]
+    L.cco_timer_start.argtypes = [C.c_void_p]
+    L.cco_timer_stop.argtypes = [C.c_void_p, p(C.c_float)]
     L.cco_result_num_matrices.argtypes = [C.c_void_p]
     L.cco_result_row_range.argtypes = [C.c_void_p, C.c_int32, p(C.c_int64), p(C.c_int64)]
     L.cco_result_matrix.argtypes = [C.c_void_p, C.c_int32, p(C.c_int64), p(C.c_int32), p(p(C.c_int64)),

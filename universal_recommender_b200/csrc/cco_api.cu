@@ -98,6 +98,7 @@ struct cco_ctx {
   size_t smem_optin = 0;
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev[8] = {};
+  cudaEvent_t tev[2] = {};
   std::vector<PinnedBuf> pinned;
   std::mutex mu;
   ncclComm_t comm = nullptr;
@@ -134,6 +135,16 @@ struct ResultMat {
   double *llr = nullptr;
   int32_t *cnt = nullptr;
 };
+struct cco_dataset {
+  cco_ctx *ctx = nullptr;
+  int n_mats = 0;
+  long long n_users = 0;
+  std::vector<long long> n_cols, nnz;
+  std::vector<long long *> rp;   // device, int64 [n_users+1]
+  std::vector<int32_t *> col;    // device
+  float ms_h2d = 0;
+};
+
 struct cco_result {
   cco_ctx *ctx = nullptr;
   std::vector<ResultMat> mats;
@@ -199,7 +210,6 @@ static int exclusive_sum_u32(cco_ctx *c, Arena &ar, const uint32_t *in, uint32_t
   void *tmp;
   CKR(ar.alloc((char **)&tmp, tb));
   CK(cub::DeviceScan::ExclusiveSum(tmp, tb, in, out, n, c->stream));
-  c->launches += 2;
   ar.release(tmp);
   return CCO_OK;
 }
@@ -209,7 +219,6 @@ static int exclusive_sum_i64(cco_ctx *c, Arena &ar, const long long *in, long lo
   void *tmp;
   CKR(ar.alloc((char **)&tmp, tb));
   CK(cub::DeviceScan::ExclusiveSum(tmp, tb, in, out, n, c->stream));
-  c->launches += 2;
   ar.release(tmp);
   return CCO_OK;
 }
@@ -230,7 +239,6 @@ static int canonicalize_device(cco_ctx *c, Arena &ar, DevRaw &m) {
   void *tmp;
   CKR(ar.alloc((char **)&tmp, tb));
   CK(cub::DeviceRadixSort::SortKeys(tmp, tb, db, m.nnz, 0, 32 + row_bits, c->stream));
-  c->launches += 8;
   ar.release(tmp);
   unsigned long long *sorted = db.Current(), *other = db.Alternate();
   uint32_t *flag, *pos;
@@ -238,13 +246,14 @@ static int canonicalize_device(cco_ctx *c, Arena &ar, DevRaw &m) {
   CKR(ar.alloc(&pos, m.nnz + 1));
   CK(cudaMemsetAsync(flag + m.nnz, 0, 4, c->stream));
   k_unique_flags<<<grid_for(m.nnz, 256, c->sm_count), 256, 0, c->stream>>>(m.nnz, sorted, flag);
+  c->launches++;
   CKR(exclusive_sum_u32(c, ar, flag, pos, m.nnz + 1));
   uint32_t n_unique = 0;
   CK(cudaMemcpyAsync(&n_unique, pos + m.nnz, 4, cudaMemcpyDeviceToHost, c->stream));
   k_unique_scatter<<<grid_for(m.nnz, 256, c->sm_count), 256, 0, c->stream>>>(m.nnz, sorted, flag, pos, other, m.col);
   CK(cudaStreamSynchronize(c->stream));
   k_rowptr_from_keys<<<grid_for(m.n_rows + 1, 256, c->sm_count), 256, 0, c->stream>>>(m.n_rows, n_unique, other, m.rp);
-  c->launches += 3;
+  c->launches += 2;
   m.nnz = n_unique;
   CK(cudaGetLastError());
   ar.release(flag);
@@ -278,12 +287,13 @@ static int downsample_device(cco_ctx *c, Arena &ar, const DevRaw &raw, const int
 
 // ---- row-kernel configurations -----------------------------------------------------------------
 struct BinCfg {
-  int threads;
-  int slots;
-  int cap;
-  int cbuf;
+  int group;    // threads that own one row: 32 (warp), 256 or 1024 (whole CTA)
+  int slots;    // table words per group
+  int cap;      // distinct keys a hashed table may hold per pass
+  int cbuf;     // candidate buffer entries per group
   bool dense;
-  size_t smem;
+  size_t region;  // shared-memory bytes per group
+  size_t smem;    // per CTA
   int ctas_per_sm;
 };
 
@@ -293,43 +303,47 @@ static int next_pow2(int x) {
   return p;
 }
 
-template <int THREADS>
-static int launch_rows_t(cco_ctx *c, const RowArgs &a, const BinCfg &cfg) {
-  int grid = c->sm_count * std::max(1, cfg.ctas_per_sm);
+template <int GROUP>
+static int launch_rows_t(cco_ctx *c, const RowArgs &a, BinCfg &cfg) {
+  constexpr int CTA = GROUP == 32 ? 256 : GROUP;
+  int occ = 1;
   if (cfg.dense) {
-    CK(cudaFuncSetAttribute(k_rows<THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
-    k_rows<THREADS, true><<<grid, THREADS, cfg.smem, c->stream>>>(a);
+    CK(cudaFuncSetAttribute(k_rows<GROUP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_rows<GROUP, true>, CTA, cfg.smem));
+    k_rows<GROUP, true><<<c->sm_count * std::max(occ, 1), CTA, cfg.smem, c->stream>>>(a);
   } else {
-    CK(cudaFuncSetAttribute(k_rows<THREADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
-    k_rows<THREADS, false><<<grid, THREADS, cfg.smem, c->stream>>>(a);
+    CK(cudaFuncSetAttribute(k_rows<GROUP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_rows<GROUP, false>, CTA, cfg.smem));
+    k_rows<GROUP, false><<<c->sm_count * std::max(occ, 1), CTA, cfg.smem, c->stream>>>(a);
   }
+  cfg.ctas_per_sm = occ;
   c->launches++;
   CK(cudaGetLastError());
   return CCO_OK;
 }
-static int launch_rows(cco_ctx *c, const RowArgs &a, const BinCfg &cfg) {
-  switch (cfg.threads) {
+static int launch_rows(cco_ctx *c, const RowArgs &a, BinCfg &cfg) {
+  switch (cfg.group) {
     case 1024: return launch_rows_t<1024>(c, a, cfg);
     case 256: return launch_rows_t<256>(c, a, cfg);
-    case 64: return launch_rows_t<64>(c, a, cfg);
+    case 32: return launch_rows_t<32>(c, a, cfg);
   }
   return set_error(CCO_E_INVALID_ARG, "internal: bad bin config");
 }
 
-static BinCfg make_cfg(cco_ctx *c, int threads, int want_slots, int top_k, int n_cols_b) {
+static BinCfg make_cfg(cco_ctx *c, int group, int want_slots, int top_k, int n_cols_b) {
   BinCfg f;
-  f.threads = threads;
-  f.cbuf = next_pow2(std::max(2 * threads, top_k + threads));
-  size_t cand_bytes = (size_t)f.cbuf * 16;
-  size_t avail = c->smem_optin - 1024;  // static shared + slack
-  int max_slots = (int)((avail - cand_bytes) / 4);
+  const int groups = group == 32 ? 8 : 1;
+  f.group = group;
+  f.cbuf = next_pow2(top_k + group);
+  size_t fixed = (size_t)f.cbuf * 16 + 3 * 256;
+  size_t avail = (c->smem_optin - 1024) / groups;  // slack for static shared memory
+  int max_slots = (int)((avail - fixed) / 4) & ~1023;
   f.slots = std::min(want_slots, max_slots);
-  f.cap = (int)(f.slots * 0.6);
+  f.cap = (int)(f.slots * 0.66);
   f.dense = n_cols_b <= f.slots;
-  f.smem = cand_bytes + (size_t)f.slots * 4;
-  size_t per_sm = 228 * 1024;
-  f.ctas_per_sm = (int)std::min<size_t>(std::min<size_t>(per_sm / (f.smem + 1024), 2048 / threads), 32);
-  if (f.ctas_per_sm < 1) f.ctas_per_sm = 1;
+  f.region = (fixed + (size_t)f.slots * 4 + 15) & ~(size_t)15;
+  f.smem = f.region * groups;
+  f.ctas_per_sm = 1;
   return f;
 }
 
@@ -408,39 +422,49 @@ static int run_indicator(cco_ctx *c, Arena &ar, const uint32_t *at_ptr, const in
     CKR(ar.alloc((char **)&tmp, tb));
     CK(cub::DeviceRadixSort::SortPairsDescending(tmp, tb, row_work + row_lo, sorted_work, ids + row_lo, rows_sorted, n_my,
                                                  0, 32, s));
-    c->launches += 6;
     ar.release(tmp);
   }
   // 2. bins -----------------------------------------------------------------------------------------
   const int k_eff = emit_all ? 1 : prm.top_k;
+  const bool warp_ok = k_eff + 32 <= 128;  // warp-owned rows keep a 128-entry candidate buffer
   BinCfg cfgL = make_cfg(c, 1024, 1 << 20, k_eff, n_cols_b);
-  BinCfg cfgM = make_cfg(c, 256, 8192, k_eff, n_cols_b);
-  BinCfg cfgS = make_cfg(c, 64, 1024, k_eff, n_cols_b);
+  BinCfg cfgC = make_cfg(c, 256, 16384, k_eff, n_cols_b);
+  BinCfg cfgWb = make_cfg(c, 32, 2048, k_eff, n_cols_b);
+  BinCfg cfgWa = make_cfg(c, 32, 512, k_eff, n_cols_b);
   // packed word: key bits must leave room for the largest possible count (= users of the item)
   int key_bits = 1;
   while (((1LL << key_bits) - 1) <= (long long)n_cols_b) ++key_bits;  // keys <= 2^kb - 2
   int count_bits = 32 - key_bits;
-  bool any_hashed = !(cfgL.dense && cfgM.dense && cfgS.dense);
-  if (any_hashed && (count_bits < 1 || (long long)max_marg_a >= (1LL << count_bits)))
+  if (count_bits < 1 || (long long)max_marg_a >= (1LL << count_bits))
     return set_error(CCO_E_UNSUPPORTED,
                      "an item with %d users and %d columns does not fit the packed 32-bit accumulator word "
                      "(key %d bits + count %d bits)", max_marg_a, n_cols_b, key_bits, count_bits);
-  // thresholds on w (descending): bin0 = multi-pass L, bin1 = L, bin2 = M, bin3 = S, tail = no work
-  auto thr = [&](const BinCfg &f) -> uint32_t { return (f.dense || n_cols_b <= f.cap) ? 0xffffffffu : (uint32_t)f.cap; };
-  // bins are chosen by WORK for parallelism; a config can only take rows whose distinct bound fits
+  // bins by WORK w (descending thresholds): 0 = multi-pass L, 1 = L (1024 threads/row), 2 = C (256 threads/row),
+  // 3 = Wb (one warp/row, 2048 slots), 4 = Wa (one warp/row, 512 slots); rows with w == 0 produce nothing.
+  auto thr = [&](const BinCfg &f) -> uint32_t { return f.dense ? 0xffffffffu : (uint32_t)f.cap; };
   uint32_t tL = thr(cfgL);
-  uint32_t tM = std::min<uint32_t>(thr(cfgM), 16384u);
-  uint32_t tS = std::min<uint32_t>(thr(cfgS), 1024u);
-  if (tM > tL) tM = tL;
-  if (tS > tM) tS = tM;
-  uint32_t h_thr[4] = {tL, tM, tS, 0u};
+  uint32_t tC = std::min<uint32_t>(thr(cfgC), 10922u);
+  uint32_t tWb = warp_ok ? std::min<uint32_t>(thr(cfgWb), 1365u) : 0u;
+  uint32_t tWa = warp_ok ? std::min<uint32_t>(thr(cfgWa), 340u) : 0u;
+  if (tC > tL) tC = tL;
+  if (tWb > tC) tWb = tC;
+  if (tWa > tWb) tWa = tWb;
+  constexpr int kBins = 5;
+  uint32_t h_thr[kBins] = {tL, tC, tWb, tWa, 0u};
   uint32_t *d_thr;
   int32_t *d_bounds;
-  CKR(ar.alloc(&d_thr, 4));
-  CKR(ar.alloc(&d_bounds, 8));
+  CKR(ar.alloc(&d_thr, kBins));
+  CKR(ar.alloc(&d_bounds, kBins + 3));
   CK(cudaMemcpyAsync(d_thr, h_thr, sizeof h_thr, cudaMemcpyHostToDevice, s));
-  k_bin_bounds<<<1, 32, 0, s>>>(n_my, sorted_work, 4, d_thr, d_bounds);
+  k_bin_bounds<<<1, 32, 0, s>>>(n_my, sorted_work, kBins, d_thr, d_bounds);
   c->launches++;
+  // per-column constants of B' for the fused LLR
+  ColTerm *col_terms;
+  CKR(ar.alloc(&col_terms, std::max<int32_t>(n_cols_b, 1)));
+  if (n_cols_b > 0) {
+    k_col_terms<<<grid_for(n_cols_b, 256, c->sm_count, 4), 256, 0, s>>>(n_cols_b, B.marg, n_users, flags, col_terms);
+    c->launches++;
+  }
   // 3. outputs ----------------------------------------------------------------------------------------
   int32_t stride = emit_all ? n_cols_b : std::min<int32_t>(prm.top_k, n_cols_b);
   if (stride < 1) stride = 1;
@@ -466,6 +490,7 @@ static int run_indicator(cco_ctx *c, Arena &ar, const uint32_t *at_ptr, const in
   a.b_col = B.col;
   a.marg_a = marg_a;
   a.marg_b = B.marg;
+  a.col_terms = col_terms;
   a.rows_sorted = rows_sorted;
   a.row_work = row_work;
   a.bin_bounds = d_bounds;
@@ -487,14 +512,16 @@ static int run_indicator(cco_ctx *c, Arena &ar, const uint32_t *at_ptr, const in
   a.emit_all = emit_all ? 1 : 0;
   CK(cudaEventRecord(c->ev[4], s));
   if (n_my > 0) {
-    const BinCfg *cfgs[4] = {&cfgL, &cfgL, &cfgM, &cfgS};
-    for (int b = 0; b < 4; ++b) {
+    BinCfg *cfgs[kBins] = {&cfgL, &cfgL, &cfgC, &cfgWb, &cfgWa};
+    for (int b = 0; b < kBins; ++b) {
+      if (b == 0 && cfgL.dense) continue;                 // dense L takes every large row in bin 1
+      if ((b == 3 || b == 4) && !warp_ok) continue;       // large top_k: the 256-thread kernel takes the small rows too
       RowArgs ab = a;
       ab.bin = b;
       ab.slots = cfgs[b]->slots;
       ab.cap = cfgs[b]->cap;
       ab.cbuf = cfgs[b]->cbuf;
-      if (b == 0 && cfgL.dense) continue;  // dense L takes every large row in bin 1 (threshold = max)
+      ab.group_smem_bytes = (int32_t)cfgs[b]->region;
       CKR(launch_rows(c, ab, *cfgs[b]));
     }
   }
@@ -538,7 +565,7 @@ static int run_indicator(cco_ctx *c, Arena &ar, const uint32_t *at_ptr, const in
   rm->llr = (double *)c->pinned_get(sizeof(double) * (size_t)std::max<long long>(total, 1));
   if (!rm->row_ptr || !rm->col || !rm->cnt || !rm->llr) return set_error(CCO_E_OOM, "pinned host allocation failed");
   CK(cudaMemcpyAsync(rm->row_ptr, out_ptr, sizeof(int64_t) * ((size_t)n_my + 1), cudaMemcpyDeviceToHost, s));
-  if (total > 0) {
+  if (total > 0 && !(flags & CCO_FLAG_RESULT_ON_DEVICE)) {
     CK(cudaMemcpyAsync(rm->col, p_col, sizeof(int32_t) * (size_t)total, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(rm->cnt, p_cnt, sizeof(int32_t) * (size_t)total, cudaMemcpyDeviceToHost, s));
     if (!emit_all) CK(cudaMemcpyAsync(rm->llr, p_llr, sizeof(double) * (size_t)total, cudaMemcpyDeviceToHost, s));
@@ -577,48 +604,94 @@ static int validate_host(int32_t n_mats, const cco_csr_t *mats, const cco_indica
   return CCO_OK;
 }
 
-static int upload(cco_ctx *c, Arena &ar, const cco_csr_t &m, DevRaw *d) {
-  d->n_rows = m.n_rows;
-  d->n_cols = m.n_cols;
-  d->nnz = m.row_ptr[m.n_rows];
-  CKR(ar.alloc(&d->rp, m.n_rows + 1));
-  CKR(ar.alloc(&d->col, std::max<long long>(d->nnz, 1)));
-  CK(cudaMemcpyAsync(d->rp, m.row_ptr, sizeof(int64_t) * ((size_t)m.n_rows + 1), cudaMemcpyHostToDevice, c->stream));
-  if (d->nnz > 0)
-    CK(cudaMemcpyAsync(d->col, m.col_idx, sizeof(int32_t) * (size_t)d->nnz, cudaMemcpyHostToDevice, c->stream));
-  return CCO_OK;
+// host CSR -> device (the dataset owns its buffers; they live until cco_dataset_free)
+static void dataset_release(cco_dataset *d) {
+  if (!d) return;
+  cudaSetDevice(d->ctx->device);
+  for (auto p : d->rp)
+    if (p) cudaFreeAsync(p, d->ctx->stream);
+  for (auto p : d->col)
+    if (p) cudaFreeAsync(p, d->ctx->stream);
+  delete d;
 }
 
-// check + (if needed) canonicalise every uploaded matrix
-static int check_and_canonicalize(cco_ctx *c, Arena &ar, std::vector<DevRaw> &raw, uint32_t flags) {
-  if (flags & CCO_FLAG_ASSUME_CANONICAL) return CCO_OK;
-  int n = (int)raw.size();
-  int *d_flags;
-  CKR(ar.alloc(&d_flags, 2 * n));
-  CK(cudaMemsetAsync(d_flags, 0, sizeof(int) * 2 * n, c->stream));
-  for (int i = 0; i < n; ++i) {
-    k_check_rows<<<grid_for(raw[i].n_rows * kSG, 256, c->sm_count), 256, 0, c->stream>>>(raw[i].n_rows, raw[i].n_cols,
-                                                                                      raw[i].rp, raw[i].col, d_flags + 2 * i);
-    c->launches++;
-  }
-  std::vector<int> h(2 * n);
-  CK(cudaMemcpyAsync(h.data(), d_flags, sizeof(int) * 2 * n, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
-  CK(cudaGetLastError());
-  for (int i = 0; i < n; ++i)
-    if (h[2 * i]) return set_error(CCO_E_INVALID_ARG, "matrix %d: row_ptr not monotone or column index out of [0, n_cols)", i);
-  for (int i = 0; i < n; ++i)
-    if (h[2 * i + 1]) CKR(canonicalize_device(c, ar, raw[i]));
-  return CCO_OK;
-}
-
-static int train_impl(cco_ctx *c, int32_t n_mats, const cco_csr_t *mats, const cco_indicator_params_t *params, int32_t seed,
-                      uint32_t flags, cco_result **out) {
-  CKR(validate_host(n_mats, mats, params));
+static int dataset_upload(cco_ctx *c, int32_t n_mats, const cco_csr_t *mats, uint32_t flags, cco_dataset **out) {
   CK(cudaSetDevice(c->device));
   cudaStream_t s = c->stream;
+  cco_dataset *d = new cco_dataset();
+  d->ctx = c;
+  d->n_mats = n_mats;
+  d->n_users = mats[0].n_rows;
+  d->rp.assign(n_mats, nullptr);
+  d->col.assign(n_mats, nullptr);
+  d->n_cols.assign(n_mats, 0);
+  d->nnz.assign(n_mats, 0);
+  struct G {
+    cco_dataset *d;
+    bool ok = false;
+    ~G() {
+      if (!ok) dataset_release(d);
+    }
+  } g{d};
+  CK(cudaEventRecord(c->ev[6], s));
+  for (int i = 0; i < n_mats; ++i) {
+    const cco_csr_t &m = mats[i];
+    d->n_cols[i] = m.n_cols;
+    d->nnz[i] = m.row_ptr[m.n_rows];
+    void *p = nullptr;
+    cudaError_t e = cudaMallocAsync(&p, sizeof(int64_t) * ((size_t)m.n_rows + 1), s);
+    if (e != cudaSuccess) return set_error(CCO_E_OOM, "cudaMallocAsync row_ptr: %s", cudaGetErrorString(e));
+    d->rp[i] = (long long *)p;
+    e = cudaMallocAsync(&p, sizeof(int32_t) * (size_t)std::max<long long>(d->nnz[i], 4), s);
+    if (e != cudaSuccess) return set_error(CCO_E_OOM, "cudaMallocAsync col_idx: %s", cudaGetErrorString(e));
+    d->col[i] = (int32_t *)p;
+    CK(cudaMemcpyAsync(d->rp[i], m.row_ptr, sizeof(int64_t) * ((size_t)m.n_rows + 1), cudaMemcpyHostToDevice, s));
+    if (d->nnz[i] > 0)
+      CK(cudaMemcpyAsync(d->col[i], m.col_idx, sizeof(int32_t) * (size_t)d->nnz[i], cudaMemcpyHostToDevice, s));
+  }
+  CK(cudaEventRecord(c->ev[7], s));
+  // check + (if needed) canonicalise in place
+  if (!(flags & CCO_FLAG_ASSUME_CANONICAL)) {
+    Arena ar(s);
+    int *d_flags;
+    CKR(ar.alloc(&d_flags, 2 * n_mats));
+    CK(cudaMemsetAsync(d_flags, 0, sizeof(int) * 2 * n_mats, s));
+    for (int i = 0; i < n_mats; ++i) {
+      k_check_rows<<<grid_for(d->n_users * kSG, 256, c->sm_count), 256, 0, s>>>(d->n_users, (int32_t)d->n_cols[i], d->rp[i],
+                                                                             d->col[i], d_flags + 2 * i);
+      c->launches++;
+    }
+    std::vector<int> h(2 * n_mats);
+    CK(cudaMemcpyAsync(h.data(), d_flags, sizeof(int) * 2 * n_mats, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    for (int i = 0; i < n_mats; ++i)
+      if (h[2 * i]) return set_error(CCO_E_INVALID_ARG, "matrix %d: row_ptr not monotone or column index out of [0, n_cols)", i);
+    for (int i = 0; i < n_mats; ++i)
+      if (h[2 * i + 1]) {
+        DevRaw r;
+        r.n_rows = d->n_users;
+        r.n_cols = (int32_t)d->n_cols[i];
+        r.nnz = d->nnz[i];
+        r.rp = d->rp[i];
+        r.col = d->col[i];
+        CKR(canonicalize_device(c, ar, r));
+        d->nnz[i] = r.nnz;
+      }
+  }
+  CK(cudaStreamSynchronize(s));
+  CK(cudaEventElapsedTime(&d->ms_h2d, c->ev[6], c->ev[7]));
+  g.ok = true;
+  *out = d;
+  return CCO_OK;
+}
+
+static int train_dataset(cco_ctx *c, const cco_dataset *ds, const cco_indicator_params_t *params, int32_t seed, uint32_t flags,
+                         cco_result **out) {
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  const int n_mats = ds->n_mats;
   Arena ar(s);
-  c->launches = 0;
   cco_result *res = new cco_result();
   res->ctx = c;
   res->mats.resize(n_mats);
@@ -632,17 +705,19 @@ static int train_impl(cco_ctx *c, int32_t n_mats, const cco_csr_t *mats, const c
   } guard{res};
   cco_stats_t &st = res->stats;
   st.n_mats = n_mats;
-  st.n_users = mats[0].n_rows;
-  const long long n_users = mats[0].n_rows;
-
-  CK(cudaEventRecord(c->ev[0], s));
+  st.n_users = ds->n_users;
+  st.ms_h2d = ds->ms_h2d;
+  const long long n_users = ds->n_users;
   std::vector<DevRaw> raw(n_mats);
   for (int i = 0; i < n_mats; ++i) {
-    CKR(upload(c, ar, mats[i], &raw[i]));
+    raw[i].n_rows = n_users;
+    raw[i].n_cols = (int32_t)ds->n_cols[i];
+    raw[i].nnz = ds->nnz[i];
+    raw[i].rp = ds->rp[i];
+    raw[i].col = ds->col[i];
     st.nnz_in_total += raw[i].nnz;
   }
   CK(cudaEventRecord(c->ev[1], s));
-  CKR(check_and_canonicalize(c, ar, raw, flags));
   // raw column counts: this rank histograms its user slice; ONE allreduce sums all matrices' counts
   long long total_cols = 0;
   std::vector<long long> col_off(n_mats + 1, 0);
@@ -667,11 +742,8 @@ static int train_impl(cco_ctx *c, int32_t n_mats, const cco_csr_t *mats, const c
   }
   // sampleDownAndBinarize every matrix
   std::vector<DevMat> dm(n_mats);
-  for (int i = 0; i < n_mats; ++i) {
+  for (int i = 0; i < n_mats; ++i)
     CKR(downsample_device(c, ar, raw[i], raw_counts + col_off[i], params[i].max_interactions, seed, flags, &dm[i]));
-    ar.release(raw[i].col);
-    ar.release(raw[i].rp);
-  }
   // `drmA.t`
   const int32_t n_items_a = dm[0].n_cols;
   uint32_t *at_ptr, *cursor;
@@ -682,7 +754,6 @@ static int train_impl(cco_ctx *c, int32_t n_mats, const cco_csr_t *mats, const c
   CKR(ar.alloc(&at_users, std::max<long long>(raw[0].nnz, 1)));
   CK(cudaMemsetAsync(d_max, 0, 4, s));
   {
-    // at_ptr = exclusive scan of colA; the scan reads one element past the end -> pad explicitly
     uint32_t *marg_pad;
     CKR(ar.alloc(&marg_pad, n_items_a + 1));
     CK(cudaMemcpyAsync(marg_pad, dm[0].marg, sizeof(int32_t) * (size_t)n_items_a, cudaMemcpyDeviceToDevice, s));
@@ -692,8 +763,11 @@ static int train_impl(cco_ctx *c, int32_t n_mats, const cco_csr_t *mats, const c
   }
   CK(cudaMemcpyAsync(cursor, at_ptr, sizeof(uint32_t) * ((size_t)n_items_a + 1), cudaMemcpyDeviceToDevice, s));
   k_transpose_scatter<<<grid_for(n_users * kSG, 256, c->sm_count), 256, 0, s>>>(n_users, dm[0].rp, dm[0].col, cursor, at_users);
-  if (n_items_a > 0) k_max_i32<<<grid_for(n_items_a, 256, c->sm_count, 2), 256, 0, s>>>(n_items_a, dm[0].marg, d_max);
-  c->launches += 2;
+  c->launches++;
+  if (n_items_a > 0) {
+    k_max_i32<<<grid_for(n_items_a, 256, c->sm_count, 2), 256, 0, s>>>(n_items_a, dm[0].marg, d_max);
+    c->launches++;
+  }
   int32_t max_marg_a = 0;
   std::vector<uint32_t> h_nnz(n_mats);
   CK(cudaMemcpyAsync(&max_marg_a, d_max, 4, cudaMemcpyDeviceToHost, s));
@@ -718,14 +792,25 @@ static int train_impl(cco_ctx *c, int32_t n_mats, const cco_csr_t *mats, const c
   }
   CK(cudaEventRecord(c->ev[3], s));
   CK(cudaStreamSynchronize(s));
-  CK(cudaEventElapsedTime(&st.ms_h2d, c->ev[0], c->ev[1]));
   CK(cudaEventElapsedTime(&st.ms_prepare, c->ev[1], c->ev[2]));
   CK(cudaEventElapsedTime(&st.ms_cooccurrence, c->ev[2], c->ev[3]));
-  CK(cudaEventElapsedTime(&st.ms_total, c->ev[0], c->ev[3]));
+  CK(cudaEventElapsedTime(&st.ms_total, c->ev[1], c->ev[3]));
+  st.ms_total += st.ms_h2d;
   st.n_kernel_launches = c->launches;
   guard.ok = true;
   *out = res;
   return CCO_OK;
+}
+
+static int train_impl(cco_ctx *c, int32_t n_mats, const cco_csr_t *mats, const cco_indicator_params_t *params, int32_t seed,
+                      uint32_t flags, cco_result **out) {
+  CKR(validate_host(n_mats, mats, params));
+  c->launches = 0;
+  cco_dataset *ds = nullptr;
+  CKR(dataset_upload(c, n_mats, mats, flags, &ds));
+  int rc = train_dataset(c, ds, params, seed, flags, out);
+  dataset_release(ds);
+  return rc;
 }
 
 }  // namespace cco
@@ -796,6 +881,7 @@ int cco_create(const cco_config_t *cfg, cco_ctx_t **out) {
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   for (auto &ev : c->ev) CK(cudaEventCreate(&ev));
+  for (auto &ev : c->tev) CK(cudaEventCreate(&ev));
   cudaMemPool_t pool;
   CK(cudaDeviceGetDefaultMemPool(&pool, cfg->device));
   uint64_t thr = UINT64_MAX;
@@ -829,6 +915,8 @@ int cco_destroy(cco_ctx_t *c) {
   if (c->comm) g_nccl.CommDestroy(c->comm);
   for (auto &b : c->pinned) cudaFreeHost(b.p);
   for (auto &ev : c->ev)
+    if (ev) cudaEventDestroy(ev);
+  for (auto &ev : c->tev)
     if (ev) cudaEventDestroy(ev);
   cudaStreamDestroy(c->stream);
   cudaStreamDestroy(c->copy_stream);
@@ -869,6 +957,46 @@ int cco_cooccurrences_idss(cco_ctx_t *ctx, int32_t n_mats, const cco_csr_t *mats
     q.min_llr = 0.0;
   }
   return cco_train(ctx, n_mats, mats, p.data(), seed, flags, out);
+}
+
+int cco_dataset_upload(cco_ctx_t *ctx, int32_t n_mats, const cco_csr_t *mats, uint32_t flags, cco_dataset_t **out) {
+  if (!ctx || !out) return set_error(CCO_E_INVALID_ARG, "null argument");
+  *out = nullptr;
+  std::vector<cco_indicator_params_t> p(std::max(n_mats, 1), cco_indicator_params_t{1, 1, 0, 0.0});
+  CKR(validate_host(n_mats, mats, p.data()));
+  return dataset_upload(ctx, n_mats, mats, flags, out);
+}
+int cco_dataset_free(cco_dataset_t *ds) {
+  dataset_release(ds);
+  return CCO_OK;
+}
+int cco_train_dataset(cco_ctx_t *ctx, const cco_dataset_t *ds, const cco_indicator_params_t *params, int32_t seed,
+                      uint32_t flags, cco_result_t **out) {
+  if (!ctx || !ds || !params || !out) return set_error(CCO_E_INVALID_ARG, "null argument");
+  if (ds->ctx != ctx) return set_error(CCO_E_INVALID_ARG, "dataset belongs to another context");
+  *out = nullptr;
+  for (int i = 0; i < ds->n_mats; ++i) {
+    if (params[i].max_interactions < 1) return set_error(CCO_E_INVALID_ARG, "matrix %d: max_interactions must be >= 1", i);
+    if (params[i].top_k < 1) return set_error(CCO_E_INVALID_ARG, "matrix %d: top_k must be >= 1", i);
+    if (params[i].top_k > CCO_MAX_TOP_K)
+      return set_error(CCO_E_UNSUPPORTED, "matrix %d: top_k %d > CCO_MAX_TOP_K (%d)", i, params[i].top_k, CCO_MAX_TOP_K);
+  }
+  ctx->launches = 0;
+  return train_dataset(ctx, ds, params, seed, flags, out);
+}
+int cco_timer_start(cco_ctx_t *ctx) {
+  if (!ctx) return set_error(CCO_E_INVALID_ARG, "null context");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventRecord(ctx->tev[0], ctx->stream));
+  return CCO_OK;
+}
+int cco_timer_stop(cco_ctx_t *ctx, float *ms) {
+  if (!ctx || !ms) return set_error(CCO_E_INVALID_ARG, "null argument");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventRecord(ctx->tev[1], ctx->stream));
+  CK(cudaEventSynchronize(ctx->tev[1]));
+  CK(cudaEventElapsedTime(ms, ctx->tev[0], ctx->tev[1]));
+  return CCO_OK;
 }
 
 int cco_result_num_matrices(const cco_result_t *r) { return r ? (int)r->mats.size() : set_error(CCO_E_INVALID_ARG, "null result"); }
@@ -942,10 +1070,13 @@ int cco_debug_downsample(cco_ctx_t *c, const cco_csr_t *m, int32_t max_interacti
   cco_indicator_params_t prm = {max_interactions, 1, 0, 0.0};
   CKR(validate_host(1, m, &prm));
   CK(cudaSetDevice(c->device));
+  cco_dataset *ds = nullptr;
+  CKR(dataset_upload(c, 1, m, flags, &ds));
+  struct DG { cco_dataset *d; ~DG() { dataset_release(d); } } dg{ds};
   Arena ar(c->stream);
   std::vector<DevRaw> raw(1);
-  CKR(upload(c, ar, *m, &raw[0]));
-  CKR(check_and_canonicalize(c, ar, raw, flags));
+  raw[0].n_rows = ds->n_users; raw[0].n_cols = (int32_t)ds->n_cols[0]; raw[0].nnz = ds->nnz[0];
+  raw[0].rp = ds->rp[0]; raw[0].col = ds->col[0];
   int32_t *counts;
   CKR(ar.alloc(&counts, std::max<int32_t>(m->n_cols, 1)));
   CK(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)std::max<int32_t>(m->n_cols, 1), c->stream));
@@ -980,11 +1111,15 @@ int cco_debug_cooccurrence(cco_ctx_t *c, const cco_csr_t *a, const cco_csr_t *b,
   CKR(validate_host(2, two, prm));
   CK(cudaSetDevice(c->device));
   cudaStream_t s = c->stream;
+  cco_dataset *ds = nullptr;
+  CKR(dataset_upload(c, 2, two, 0, &ds));
+  struct DG { cco_dataset *d; ~DG() { dataset_release(d); } } dg{ds};
   Arena ar(s);
   std::vector<DevRaw> raw(2);
-  CKR(upload(c, ar, two[0], &raw[0]));
-  CKR(upload(c, ar, two[1], &raw[1]));
-  CKR(check_and_canonicalize(c, ar, raw, 0));
+  for (int i = 0; i < 2; ++i) {
+    raw[i].n_rows = ds->n_users; raw[i].n_cols = (int32_t)ds->n_cols[i]; raw[i].nnz = ds->nnz[i];
+    raw[i].rp = ds->rp[i]; raw[i].col = ds->col[i];
+  }
   // identity "downsample" (m = INT_MAX) gives the device CSR + marginals
   std::vector<DevMat> dm(2);
   for (int i = 0; i < 2; ++i) {

@@ -42,7 +42,9 @@ struct RowArgs {
   int32_t count_bits;  // packed hash word = (key << count_bits) | count
   int32_t slots;       // hash/dense table words in shared memory
   int32_t cap;         // max distinct keys per pass for hashed rows (load-factor bound)
-  int32_t cbuf;        // candidate buffer entries (power of two, >= 2*top_k)
+  int32_t cbuf;        // candidate buffer entries per group (power of two, >= top_k + GROUP)
+  int32_t group_smem_bytes;  // shared memory of one group (multiple of 16)
+  const struct ColTerm *col_terms;  // per column of B': {columnEntropy, colB}
   // outputs, strided
   int32_t out_stride;
   int32_t *out_col;
@@ -290,80 +292,112 @@ __global__ void k_bin_bounds(int32_t n_rows, const uint32_t *__restrict__ sorted
 }
 
 // ------------------------------------------------------------------------------------------------
-// The fused row kernel: one CTA per primary item a.
-//   count : for u in users(a): for b in B'[u]: table[b]++            (shared-memory accumulator)
-//   score : for every touched b: LLR(k11, colA[a], colB[b], N) in fp64, fused, in registers
-//   select: running top-k under the total order (llr desc, col asc)  (candidate buffer + prune)
-// DENSE: the table is indexed by b directly (n_cols_b <= slots); otherwise a packed open-addressing
-// hash (key << count_bits | count), multi-pass over hash partitions when the row's distinct-cell
-// bound exceeds the table capacity.
+// Per-column constants of B' for the fused LLR: columnEntropy = entropy(cb, N - cb) depends only on the
+// column, so it is evaluated once per column (same operations, same bits) instead of once per cell.
 // ------------------------------------------------------------------------------------------------
-struct Cand {
-  unsigned long long key;  // bit pattern of the (positive) fp64 LLR: monotone
-  uint32_t col;
-  uint32_t cnt;
+struct __align__(16) ColTerm {
+  double col_e;
+  int32_t cb;
+  int32_t pad;
 };
+__global__ void k_col_terms(int32_t n_cols, const int32_t *__restrict__ marg, long long n_users, uint32_t flags,
+                            ColTerm *__restrict__ out) {
+  const bool varargs = (flags & CCO_FLAG_ENTROPY_VARARGS) != 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_cols; i += gridDim.x * blockDim.x) {
+    long long cb = marg[i];
+    ColTerm t;
+    t.col_e = entropy2(cb, n_users - cb, varargs);
+    t.cb = (int32_t)cb;
+    t.pad = 0;
+    out[i] = t;
+  }
+}
 
+// ------------------------------------------------------------------------------------------------
+// The fused row kernel.  A GROUP of threads (one warp, or a whole CTA of 256 / 1024 threads) owns one
+// primary item a at a time and keeps everything for that row in shared memory:
+//   count  : for u in users(a): for b in B'[u]: table[b]++     32-user chunks per warp, products flattened
+//                                                               over lanes by a warp prefix-sum + shuffle search
+//   compact: occupied table words -> dense per-warp lists (in place)
+//   score  : LLR(k11, colA[a], colB[b], N) in fp64, in registers, 2 logs per cell (the other xLogX terms
+//            are per-row / per-column / small-integer tables holding bit-identical values)
+//   select : running top-k under the total order (llr desc, col asc): threshold-pruned candidate buffer
+// DENSE: table indexed by b directly (n_cols_b <= slots); otherwise a packed open-addressing hash
+// (key << count_bits | count), multi-pass over hash partitions when the row's distinct-cell bound
+// exceeds the table capacity.  Nothing of A'^T B' is ever written to HBM except the kept top-k.
+// ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool cand_better(unsigned long long ka, uint32_t ca, unsigned long long kb, uint32_t cb) {
   return ka > kb || (ka == kb && ca < cb);
 }
 
-template <int THREADS>
-__device__ void sort_candidates(unsigned long long *ckey, uint32_t *ccol, uint32_t *ccnt, int n) {
-  // bitonic sort, best first; pads [n, n2) with key 0 (never a valid candidate: LLR > 0)
+template <int GROUP>
+__device__ __forceinline__ void group_sync() {
+  if (GROUP == 32) __syncwarp(); else __syncthreads();
+}
+
+// bitonic sort of the candidate buffer, best first; pads [n, n2) with key 0 (never valid: LLR > 0)
+template <int GROUP>
+__device__ void sort_candidates(unsigned long long *ckey, uint32_t *ccol, uint32_t *ccnt, int n, int gtid) {
   int n2 = 1;
   while (n2 < n) n2 <<= 1;
-  for (int i = n + threadIdx.x; i < n2; i += THREADS) { ckey[i] = 0ULL; ccol[i] = 0xffffffffu; ccnt[i] = 0; }
-  __syncthreads();
+  for (int i = n + gtid; i < n2; i += GROUP) { ckey[i] = 0ULL; ccol[i] = 0xffffffffu; ccnt[i] = 0; }
+  group_sync<GROUP>();
   for (int k2 = 2; k2 <= n2; k2 <<= 1) {
     for (int j = k2 >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < n2; i += THREADS) {
-        int p = i ^ j;
-        if (p > i) {
-          bool up = (i & k2) == 0;  // this sub-sequence sorted best-first
-          unsigned long long ki = ckey[i], kp = ckey[p];
-          uint32_t ci = ccol[i], cp = ccol[p];
-          bool swap = up ? cand_better(kp, cp, ki, ci) : cand_better(ki, ci, kp, cp);
-          if (swap) {
-            ckey[i] = kp; ckey[p] = ki;
-            ccol[i] = cp; ccol[p] = ci;
-            uint32_t t = ccnt[i]; ccnt[i] = ccnt[p]; ccnt[p] = t;
-          }
+      for (int t = gtid; t < (n2 >> 1); t += GROUP) {
+        // t-th compare-exchange pair of this step
+        int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        int p = i | j;
+        bool up = (i & k2) == 0;
+        unsigned long long ki = ckey[i], kp = ckey[p];
+        uint32_t ci = ccol[i], cp = ccol[p];
+        bool swap = up ? cand_better(kp, cp, ki, ci) : cand_better(ki, ci, kp, cp);
+        if (swap) {
+          ckey[i] = kp; ckey[p] = ki;
+          ccol[i] = cp; ccol[p] = ci;
+          uint32_t tmp = ccnt[i]; ccnt[i] = ccnt[p]; ccnt[p] = tmp;
         }
       }
-      __syncthreads();
+      group_sync<GROUP>();
     }
   }
 }
 
-template <int THREADS, bool DENSE>
-__global__ void __launch_bounds__(THREADS) k_rows(const RowArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  // layout: ckey[cbuf] (8B) | ccol[cbuf] | ccnt[cbuf] | table[slots]
-  unsigned long long *ckey = reinterpret_cast<unsigned long long *>(smem_raw);
-  uint32_t *ccol = reinterpret_cast<uint32_t *>(ckey + a.cbuf);
-  uint32_t *ccnt = ccol + a.cbuf;
-  uint32_t *table = ccnt + a.cbuf;
-  __shared__ int s_ncand;
-  __shared__ unsigned long long s_thr_key;
-  __shared__ uint32_t s_thr_col;
-  __shared__ int s_have_thr;
+constexpr int kX12N = 31;  // x12tab[j] = xLogX(ra - j) for j < 31; x12tab[31] = xLogX(N - ra)
 
-  const int tid = threadIdx.x;
-  const int lane = tid & 31;
+template <int GROUP, bool DENSE>
+__global__ void __launch_bounds__(GROUP == 32 ? 256 : GROUP) k_rows(const RowArgs a) {
+  constexpr int CTA = GROUP == 32 ? 256 : GROUP;
+  constexpr int GROUPS = CTA / GROUP;
+  constexpr int NW = GROUP / 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int gid = tid / GROUP, gtid = tid % GROUP, gw = gtid >> 5;
+  unsigned char *base = smem_raw + (size_t)gid * a.group_smem_bytes;
+  unsigned long long *tk_key = reinterpret_cast<unsigned long long *>(base);
+  uint32_t *tk_col = reinterpret_cast<uint32_t *>(tk_key + a.cbuf);
+  uint32_t *tk_cnt = tk_col + a.cbuf;
+  double *x12tab = reinterpret_cast<double *>(tk_cnt + a.cbuf);
+  double *x11tab = x12tab + 32;
+  int *ctrl = reinterpret_cast<int *>(x11tab + 32);  // [0] ncand [1] have_thr [2,3] thr_key [4] thr_col [8..8+NW) per-warp list sizes
+  uint32_t *table = reinterpret_cast<uint32_t *>(ctrl + 64);
+  volatile int *vctrl = ctrl;
+
   const int row_begin = a.bin_bounds[a.bin], row_end = a.bin_bounds[a.bin + 1];
   const bool varargs = (a.flags & CCO_FLAG_ENTROPY_VARARGS) != 0;
   const int cbits = a.count_bits;
-  const uint32_t cmask = (cbits >= 32) ? 0xffffffffu : ((1u << cbits) - 1u);
+  const uint32_t cmask = (1u << cbits) - 1u;
   const uint32_t slots = (uint32_t)a.slots;
-  const int prune_limit = a.cbuf - THREADS;
+  const int prune_limit = a.cbuf - GROUP;
+  const long long N = a.n_users;
+  const double xN = xlogx(N);
   unsigned long long distinct_local = 0;
+  if (gtid < 32) x11tab[gtid] = xlogx((long long)gtid);
 
-  for (int ri = row_begin + blockIdx.x; ri < row_end; ri += gridDim.x) {
+  for (int ri = row_begin + blockIdx.x * GROUPS + gid; ri < row_end; ri += gridDim.x * GROUPS) {
     const int item = a.rows_sorted[ri];
     const uint32_t u_begin = a.at_ptr[item], u_end = a.at_ptr[item + 1];
     const long long ra = a.marg_a[item];
-    const double row_e = entropy2(ra, a.n_users - ra, varargs);
     uint32_t n_pass = 1;
     if (!DENSE) {
       uint32_t w = a.row_work[item];
@@ -371,130 +405,197 @@ __global__ void __launch_bounds__(THREADS) k_rows(const RowArgs a) {
       n_pass = (dbound + (uint32_t)a.cap - 1u) / (uint32_t)a.cap;
       if (n_pass == 0) n_pass = 1;
     }
-    if (tid == 0) { s_ncand = 0; s_have_thr = 0; }
-    int emit_cursor_base = 0;
+    group_sync<GROUP>();  // previous row fully done with smem
+    if (gtid < 32) {
+      long long v = (gtid < kX12N) ? ra - gtid : N - ra;
+      x12tab[gtid] = v >= 0 ? xlogx(v) : 0.0;
+    }
+    if (gtid == 0) { ctrl[0] = 0; ctrl[1] = 0; }
+    int emitted = 0;
 
     for (uint32_t pass = 0; pass < n_pass; ++pass) {
-      // ---- clear --------------------------------------------------------------------------------
-      for (uint32_t i = tid; i < slots; i += THREADS) table[i] = DENSE ? 0u : kEmpty;
-      __syncthreads();
-      // ---- count --------------------------------------------------------------------------------
-      {
-        constexpr int SG = 8;  // lanes per user
-        const int sg = tid / SG, sl = tid % SG;
-        for (uint32_t i = u_begin + sg; i < u_end; i += THREADS / SG) {
+      // ---- clear --------------------------------------------------------------------------------------
+      const uint32_t clear_n = DENSE ? (uint32_t)a.n_cols_b : slots;
+      for (uint32_t i = gtid; i < clear_n; i += GROUP) table[i] = DENSE ? 0u : kEmpty;
+      group_sync<GROUP>();
+      // ---- count: each warp takes 32-user chunks; products of a chunk are flattened over the lanes -----
+      for (uint32_t c0 = u_begin + gw * 32; c0 < u_end; c0 += NW * 32) {
+        const uint32_t i = c0 + lane;
+        uint32_t s = 0, len = 0;
+        if (i < u_end) {
           const int32_t u = a.at_users[i];
-          const uint32_t s = a.b_ptr[u], e = a.b_ptr[u + 1];
-          for (uint32_t q = s + sl; q < e; q += SG) {
-            const uint32_t b = (uint32_t)a.b_col[q];
+          s = a.b_ptr[u];
+          len = a.b_ptr[u + 1] - s;
+        }
+        uint32_t off = len;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          uint32_t v = __shfl_up_sync(0xffffffffu, off, d);
+          if (lane >= d) off += v;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, off, 31);
+        off -= len;  // exclusive
+        for (uint32_t p0 = 0; p0 < total; p0 += 32) {
+          const uint32_t p = p0 + lane;
+          int j = 0;
+#pragma unroll
+          for (int st = 16; st > 0; st >>= 1) {
+            const int c = j + st;
+            const uint32_t v = __shfl_sync(0xffffffffu, off, c);
+            if (v <= p) j = c;
+          }
+          const uint32_t sj = __shfl_sync(0xffffffffu, s, j), oj = __shfl_sync(0xffffffffu, off, j);
+          if (p < total) {
+            const uint32_t b = (uint32_t)a.b_col[sj + (p - oj)];
             if (DENSE) {
               atomicAdd(&table[b], 1u);
             } else {
               const uint32_t h = hash32(b);
-              if (n_pass > 1 && (h % n_pass) != pass) continue;
-              uint32_t slot = __umulhi(h * 0x9e3779b1u, slots);
-              const uint32_t want = b << cbits;
-              uint32_t probes = 0;
-              while (true) {
-                uint32_t w = *reinterpret_cast<volatile uint32_t *>(&table[slot]);
-                if ((w >> cbits) == b && w != kEmpty) { atomicAdd(&table[slot], 1u); break; }
-                if (w == kEmpty) {
-                  uint32_t old = atomicCAS(&table[slot], kEmpty, want | 1u);
-                  if (old == kEmpty) break;
-                  if ((old >> cbits) == b) { atomicAdd(&table[slot], 1u); break; }
+              if (n_pass == 1 || (h % n_pass) == pass) {
+                uint32_t slot = __umulhi(h * 0x9e3779b1u, slots);
+                const uint32_t want = b << cbits;
+                uint32_t probes = 0;
+                while (true) {
+                  uint32_t w = *reinterpret_cast<volatile uint32_t *>(&table[slot]);
+                  if ((w >> cbits) == b && w != kEmpty) { atomicAdd(&table[slot], 1u); break; }
+                  if (w == kEmpty) {
+                    uint32_t old = atomicCAS(&table[slot], kEmpty, want | 1u);
+                    if (old == kEmpty) break;
+                    if ((old >> cbits) == b) { atomicAdd(&table[slot], 1u); break; }
+                  }
+                  slot = (slot + 1 == slots) ? 0 : slot + 1;
+                  if (++probes > slots) { atomicOr(a.err_flag, 1); break; }
                 }
-                slot = (slot + 1 == slots) ? 0 : slot + 1;
-                if (++probes > slots) { atomicOr(a.err_flag, 1); break; }
               }
             }
           }
         }
       }
-      __syncthreads();
-      // ---- score + select -------------------------------------------------------------------------
+      group_sync<GROUP>();
+      // ---- compact: each warp packs the occupied words of its own table segment, in place ----------------
       const uint32_t scan_n = DENSE ? (uint32_t)a.n_cols_b : slots;
-      for (uint32_t base = 0; base < scan_n; base += THREADS) {
-        const uint32_t slot = base + tid;
-        uint32_t b = 0, k11 = 0;
-        bool valid = false;
-        if (slot < scan_n) {
-          uint32_t w = table[slot];
-          if (DENSE) { valid = w != 0; b = slot; k11 = w; }
-          else { valid = w != kEmpty; b = w >> cbits; k11 = w & cmask; }
-        }
-        if (valid) ++distinct_local;
-        unsigned long long key = 0;
-        bool pass_ok = false;
-        if (a.emit_all) {
-          pass_ok = valid;
-        } else if (valid && !(a.self && (int)b == item)) {
-          const long long cb = a.marg_b[b];
-          double v = llr_hoisted((long long)k11, ra, cb, a.n_users, row_e, varargs);
-          pass_ok = v > 0.0 && (!a.has_min_llr || v >= a.min_llr);
-          key = (unsigned long long)__double_as_longlong(v);
-          if (pass_ok && s_have_thr) pass_ok = cand_better(key, b, s_thr_key, s_thr_col);
-        }
-        // warp-aggregated append
-        unsigned m = __ballot_sync(0xffffffffu, pass_ok);
-        if (m) {
-          int basepos = 0;
-          if (lane == 0) basepos = atomicAdd(&s_ncand, __popc(m));
-          basepos = __shfl_sync(0xffffffffu, basepos, 0);
-          if (pass_ok) {
-            int pos = basepos + __popc(m & ((1u << lane) - 1u));
-            if (a.emit_all) {
-              size_t o = (size_t)item * a.out_stride + emit_cursor_base + pos;
-              a.out_col[o] = (int32_t)b;
-              a.out_cnt[o] = (int32_t)k11;
-            } else {
-              ckey[pos] = key; ccol[pos] = b; ccnt[pos] = k11;
-            }
-          }
-        }
-        __syncthreads();
-        if (!a.emit_all) {
-          int n = s_ncand;
-          if (n > prune_limit) {
-            sort_candidates<THREADS>(ckey, ccol, ccnt, n);
-            if (tid == 0) {
-              int keep = n < a.top_k ? n : a.top_k;
-              s_ncand = keep;
-              if (n >= a.top_k) { s_thr_key = ckey[a.top_k - 1]; s_thr_col = ccol[a.top_k - 1]; s_have_thr = 1; }
-            }
-            __syncthreads();
-          }
-        }
+      const uint32_t seg = (((scan_n + NW - 1) / NW) + 31u) & ~31u;
+      const uint32_t seg_lo = min((uint32_t)gw * seg, scan_n), seg_hi = min(seg_lo + seg, scan_n);
+      uint32_t n_mine = 0;
+      for (uint32_t pos = seg_lo; pos < seg_hi; pos += 32) {
+        const uint32_t idx = pos + lane;
+        uint32_t w = DENSE ? 0u : kEmpty;
+        if (idx < seg_hi) w = table[idx];
+        const bool valid = DENSE ? (w != 0u) : (w != kEmpty);
+        const uint32_t word = DENSE ? ((idx << cbits) | w) : w;
+        const unsigned m = __ballot_sync(0xffffffffu, valid);
+        __syncwarp();
+        if (valid) table[seg_lo + n_mine + __popc(m & ((1u << lane) - 1u))] = word;
+        n_mine += __popc(m);
+        __syncwarp();
+      }
+      if (lane == 0) { distinct_local += n_mine; if (NW > 1) ctrl[8 + gw] = (int)n_mine; }
+      int iters = (int)((n_mine + 31) / 32);
+      if (NW > 1) {
+        group_sync<GROUP>();
+        iters = 0;
+        for (int w2 = 0; w2 < NW; ++w2) iters = max(iters, (vctrl[8 + w2] + 31) / 32);
       }
       if (a.emit_all) {
-        __syncthreads();
-        emit_cursor_base += s_ncand;
-        __syncthreads();
-        if (tid == 0) s_ncand = 0;
-      }
-      __syncthreads();
-    }
-    // ---- final select + write -------------------------------------------------------------------
-    if (a.emit_all) {
-      if (tid == 0) a.out_len[item] = emit_cursor_base;
-    } else {
-      int n = s_ncand;
-      if (n > 0) {
-        sort_candidates<THREADS>(ckey, ccol, ccnt, n);
-        int keep = n < a.top_k ? n : a.top_k;
-        for (int i = tid; i < keep; i += THREADS) {
-          size_t o = (size_t)item * a.out_stride + i;
-          a.out_col[o] = (int32_t)ccol[i];
-          a.out_llr[o] = __longlong_as_double((long long)ckey[i]);
-          a.out_cnt[o] = (int32_t)ccnt[i];
+        // debug: every non-zero cell of the row (col, count), unordered
+        int basepos = 0;
+        if (lane == 0) basepos = atomicAdd(&ctrl[0], (int)n_mine);
+        basepos = __shfl_sync(0xffffffffu, basepos, 0);
+        for (uint32_t q = lane; q < n_mine; q += 32) {
+          const uint32_t word = table[seg_lo + q];
+          const size_t o = (size_t)item * a.out_stride + emitted + basepos + q;
+          a.out_col[o] = (int32_t)(word >> cbits);
+          a.out_cnt[o] = (int32_t)(word & cmask);
         }
-        if (tid == 0) a.out_len[item] = keep;
-      } else if (tid == 0) {
+        group_sync<GROUP>();
+        emitted += vctrl[0];
+        group_sync<GROUP>();
+        if (gtid == 0) ctrl[0] = 0;
+        group_sync<GROUP>();
+        continue;
+      }
+      // ---- score + select -----------------------------------------------------------------------------------
+      const double x_ra = x12tab[0], x_nra = x12tab[kX12N];
+      const double row_e = varargs ? __dsub_rn(xN, __dadd_rn(__dadd_rn(0.0, x_ra), x_nra))
+                                   : __dsub_rn(__dsub_rn(xN, x_ra), x_nra);
+      for (int it = 0; it < iters; ++it) {
+        const uint32_t q = (uint32_t)it * 32 + lane;
+        bool pass_ok = false;
+        unsigned long long key = 0;
+        uint32_t b = 0, k11 = 0;
+        if (q < n_mine) {
+          const uint32_t word = table[seg_lo + q];
+          b = word >> cbits;
+          k11 = word & cmask;
+          if (!(a.self && (int)b == item)) {
+            const ColTerm ct = a.col_terms[b];
+            const long long cb = ct.cb;
+            const long long k21 = cb - k11, k22 = N - ra - cb + k11;
+            const double x11 = k11 < 32 ? x11tab[k11] : xlogx((long long)k11);
+            const double x12 = k11 < kX12N ? x12tab[k11] : xlogx(ra - k11);
+            const double x21 = xlogx(k21), x22 = xlogx(k22);
+            double mat_e;
+            if (varargs)
+              mat_e = __dsub_rn(xN, __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(0.0, x11), x12), x21), x22));
+            else
+              mat_e = __dsub_rn(__dsub_rn(__dsub_rn(__dsub_rn(xN, x11), x12), x21), x22);
+            const double s = __dadd_rn(row_e, ct.col_e);
+            const double v = (s < mat_e) ? 0.0 : __dmul_rn(2.0, __dsub_rn(s, mat_e));
+            pass_ok = v > 0.0 && (!a.has_min_llr || v >= a.min_llr);
+            key = (unsigned long long)__double_as_longlong(v);
+            if (pass_ok && vctrl[1]) {
+              const unsigned long long tk = *reinterpret_cast<volatile unsigned long long *>(&ctrl[2]);
+              pass_ok = cand_better(key, b, tk, (uint32_t)vctrl[4]);
+            }
+          }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, pass_ok);
+        if (m) {
+          int basepos = 0;
+          if (lane == 0) basepos = atomicAdd(&ctrl[0], __popc(m));
+          basepos = __shfl_sync(0xffffffffu, basepos, 0);
+          if (pass_ok) {
+            const int pos = basepos + __popc(m & ((1u << lane) - 1u));
+            tk_key[pos] = key; tk_col[pos] = b; tk_cnt[pos] = k11;
+          }
+        }
+        group_sync<GROUP>();
+        const int n = vctrl[0];
+        if (n > prune_limit) {
+          sort_candidates<GROUP>(tk_key, tk_col, tk_cnt, n, gtid);
+          if (gtid == 0) {
+            ctrl[0] = n < a.top_k ? n : a.top_k;
+            if (n >= a.top_k) {
+              *reinterpret_cast<unsigned long long *>(&ctrl[2]) = tk_key[a.top_k - 1];
+              ctrl[4] = (int)tk_col[a.top_k - 1];
+              ctrl[1] = 1;
+            }
+          }
+          group_sync<GROUP>();
+        }
+      }
+      group_sync<GROUP>();
+    }
+    // ---- final select + write -------------------------------------------------------------------------------
+    if (a.emit_all) {
+      if (gtid == 0) a.out_len[item] = emitted;
+    } else {
+      const int n = vctrl[0];
+      if (n > 0) {
+        sort_candidates<GROUP>(tk_key, tk_col, tk_cnt, n, gtid);
+        const int keep = n < a.top_k ? n : a.top_k;
+        for (int i = gtid; i < keep; i += GROUP) {
+          const size_t o = (size_t)item * a.out_stride + i;
+          a.out_col[o] = (int32_t)tk_col[i];
+          a.out_llr[o] = __longlong_as_double((long long)tk_key[i]);
+          a.out_cnt[o] = (int32_t)tk_cnt[i];
+        }
+        if (gtid == 0) a.out_len[item] = keep;
+      } else if (gtid == 0) {
         a.out_len[item] = 0;
       }
     }
-    __syncthreads();
   }
-  // stats: distinct cells visited by this CTA
   for (int o = 16; o > 0; o >>= 1) distinct_local += __shfl_xor_sync(0xffffffffu, distinct_local, o);
   if (lane == 0 && distinct_local) atomicAdd(a.stat_distinct, distinct_local);
 }

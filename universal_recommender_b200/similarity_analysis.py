@@ -61,6 +61,7 @@ class CcoContext:
         self._h = h
         self.rank, self.world_size, self.device = rank, world_size, device
         self.last_stats: TrainStats | None = None
+        self._pinned_addr: dict = {}
 
     @staticmethod
     def nccl_unique_id() -> bytes:
@@ -92,23 +93,16 @@ class CcoContext:
         N.check(self._L.cco_host_alloc(self._h, max(n, 1) * dt.itemsize, C.byref(p)))
         buf = (C.c_byte * (max(n, 1) * dt.itemsize)).from_address(p.value)
         arr = np.frombuffer(buf, dtype=dt, count=n)
-        arr._cco_pinned = p  # keep the address for host_free
+        self._pinned_addr[arr.ctypes.data if n else p.value] = p
         return arr
 
     def host_free(self, arr: np.ndarray):
-        base = arr
-        while getattr(base, "_cco_pinned", None) is None and base.base is not None:
-            base = base.base
-        p = getattr(base, "_cco_pinned", None)
+        p = self._pinned_addr.pop(arr.ctypes.data, None)
         if p is not None:
             self._L.cco_host_free(self._h, p)
 
     # ---- the hot path ---------------------------------------------------------------------------------------
-    def train_csr(self, mats: Sequence[tuple[int, int, np.ndarray, np.ndarray]], params: Sequence[tuple[int, int, Optional[float]]],
-                  seed: int, flags: int = 0):
-        """Raw entry: mats = [(n_rows, n_cols, row_ptr int64, col_idx int32)], params = [(m, k, minLLR|None)].
-        -> list of (row_begin, row_end, n_cols, row_ptr, col_idx, llr, count) numpy copies, one per matrix."""
-        L = self._L
+    def _csr_array(self, mats):
         n = len(mats)
         keep = []
         cm = (N.CsrT * n)()
@@ -117,10 +111,15 @@ class CcoContext:
             ci = np.ascontiguousarray(ci, dtype=np.int32)
             keep.append((rp, ci))
             cm[i] = N.as_csr_t(nr, nc, rp, ci)
-        cp = (N.ParamsT * n)(*[N.ParamsT(int(m), int(k), 0 if ml is None else 1, 0.0 if ml is None else float(ml))
-                               for (m, k, ml) in params])
-        res = C.c_void_p()
-        N.check(L.cco_train(self._h, n, cm, cp, C.c_int32(_to_i32(seed)), flags, C.byref(res)))
+        return cm, keep
+
+    @staticmethod
+    def _params_array(params):
+        return (N.ParamsT * len(params))(*[N.ParamsT(int(m), int(k), 0 if ml is None else 1, 0.0 if ml is None else float(ml))
+                                           for (m, k, ml) in params])
+
+    def _collect(self, res, n, copy_arrays=True):
+        L = self._L
         try:
             out = []
             for i in range(n):
@@ -131,7 +130,7 @@ class CcoContext:
                 N.check(L.cco_result_matrix(res, i, C.byref(nr), C.byref(nc), C.byref(prp), C.byref(pci), C.byref(pll), C.byref(pcn)))
                 rp = np.ctypeslib.as_array(prp, shape=(nr.value + 1,)).copy()
                 nnz = int(rp[-1])
-                if nnz:
+                if nnz and copy_arrays:
                     ci = np.ctypeslib.as_array(pci, shape=(nnz,)).copy()
                     ll = np.ctypeslib.as_array(pll, shape=(nnz,)).copy()
                     cn = np.ctypeslib.as_array(pcn, shape=(nnz,)).copy()
@@ -146,6 +145,40 @@ class CcoContext:
             return out
         finally:
             L.cco_result_free(res)
+
+    def train_csr(self, mats: Sequence[tuple[int, int, np.ndarray, np.ndarray]], params: Sequence[tuple[int, int, Optional[float]]],
+                  seed: int, flags: int = 0, copy_arrays: bool = True):
+        """Raw entry (cco_train): mats = [(n_rows, n_cols, row_ptr int64, col_idx int32)], params = [(m, k, minLLR|None)].
+        -> list of (row_begin, row_end, n_cols, row_ptr, col_idx, llr, count) numpy copies, one per matrix."""
+        cm, keep = self._csr_array(mats)
+        res = C.c_void_p()
+        N.check(self._L.cco_train(self._h, len(mats), cm, self._params_array(params), C.c_int32(_to_i32(seed)), flags,
+                                  C.byref(res)))
+        return self._collect(res, len(mats), copy_arrays)
+
+    # ---- split form: matrices resident in HBM across trains ---------------------------------------------
+    def upload(self, mats, flags: int = 0):
+        cm, keep = self._csr_array(mats)
+        ds = C.c_void_p()
+        N.check(self._L.cco_dataset_upload(self._h, len(mats), cm, flags, C.byref(ds)))
+        return (ds, len(mats))
+
+    def train_dataset(self, dataset, params, seed: int, flags: int = 0, copy_arrays: bool = True):
+        ds, n = dataset
+        res = C.c_void_p()
+        N.check(self._L.cco_train_dataset(self._h, ds, self._params_array(params), C.c_int32(_to_i32(seed)), flags, C.byref(res)))
+        return self._collect(res, n, copy_arrays)
+
+    def free_dataset(self, dataset):
+        self._L.cco_dataset_free(dataset[0])
+
+    def timer_start(self):
+        N.check(self._L.cco_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        N.check(self._L.cco_timer_stop(self._h, C.byref(ms)))
+        return ms.value
 
     # ---- debug / parity entries ---------------------------------------------------------------------------
     def debug_llr(self, k11, k12, k21, k22, flags: int = 0) -> np.ndarray:
