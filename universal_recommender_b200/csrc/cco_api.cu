@@ -291,6 +291,7 @@ struct BinCfg {
   int slots;    // table words per group
   int cap;      // distinct keys a hashed table may hold per pass
   int cbuf;     // candidate buffer entries per group
+  int caux, keep_max, final_max;
   bool dense;
   size_t region;  // shared-memory bytes per group
   size_t smem;    // per CTA
@@ -325,6 +326,7 @@ static int launch_rows(cco_ctx *c, const RowArgs &a, BinCfg &cfg) {
   switch (cfg.group) {
     case 1024: return launch_rows_t<1024>(c, a, cfg);
     case 256: return launch_rows_t<256>(c, a, cfg);
+    case 128: return launch_rows_t<128>(c, a, cfg);
     case 32: return launch_rows_t<32>(c, a, cfg);
   }
   return set_error(CCO_E_INVALID_ARG, "internal: bad bin config");
@@ -334,12 +336,15 @@ static BinCfg make_cfg(cco_ctx *c, int group, int want_slots, int top_k, int n_c
   BinCfg f;
   const int groups = group == 32 ? 8 : 1;
   f.group = group;
-  f.cbuf = next_pow2(top_k + group);
-  size_t fixed = (size_t)f.cbuf * 16 + 3 * 256;
+  f.cbuf = next_pow2(top_k + std::max(group, 128) + (group == 32 ? 64 : 0));
+  f.final_max = next_pow2(top_k);
+  f.keep_max = std::max(f.final_max, (f.cbuf - group) / 2);
+  f.caux = group == 32 ? 0 : f.keep_max;
+  size_t fixed = (size_t)(f.cbuf + f.caux) * 16 + 3 * 256 + 1024;
   size_t avail = (c->smem_optin - 1024) / groups;  // slack for static shared memory
   int max_slots = (int)((avail - fixed) / 4) & ~1023;
   f.slots = std::min(want_slots, max_slots);
-  f.cap = (int)(f.slots * 0.66);
+  f.cap = f.slots / 2;
   f.dense = n_cols_b <= f.slots;
   f.region = (fixed + (size_t)f.slots * 4 + 15) & ~(size_t)15;
   f.smem = f.region * groups;
@@ -426,11 +431,11 @@ static int run_indicator(cco_ctx *c, Arena &ar, const uint32_t *at_ptr, const in
   }
   // 2. bins -----------------------------------------------------------------------------------------
   const int k_eff = emit_all ? 1 : prm.top_k;
-  const bool warp_ok = k_eff + 32 <= 128;  // warp-owned rows keep a 128-entry candidate buffer
+  const bool warp_ok = k_eff + 32 <= 256;  // warp-owned rows keep a 256-entry candidate buffer
   BinCfg cfgL = make_cfg(c, 1024, 1 << 20, k_eff, n_cols_b);
   BinCfg cfgC = make_cfg(c, 256, 16384, k_eff, n_cols_b);
-  BinCfg cfgWb = make_cfg(c, 32, 2048, k_eff, n_cols_b);
-  BinCfg cfgWa = make_cfg(c, 32, 512, k_eff, n_cols_b);
+  BinCfg cfgG = make_cfg(c, 128, 4096, k_eff, n_cols_b);
+  BinCfg cfgW = make_cfg(c, 32, 512, k_eff, n_cols_b);
   // packed word: key bits must leave room for the largest possible count (= users of the item)
   int key_bits = 1;
   while (((1LL << key_bits) - 1) <= (long long)n_cols_b) ++key_bits;  // keys <= 2^kb - 2
@@ -440,12 +445,12 @@ static int run_indicator(cco_ctx *c, Arena &ar, const uint32_t *at_ptr, const in
                      "an item with %d users and %d columns does not fit the packed 32-bit accumulator word "
                      "(key %d bits + count %d bits)", max_marg_a, n_cols_b, key_bits, count_bits);
   // bins by WORK w (descending thresholds): 0 = multi-pass L, 1 = L (1024 threads/row), 2 = C (256 threads/row),
-  // 3 = Wb (one warp/row, 2048 slots), 4 = Wa (one warp/row, 512 slots); rows with w == 0 produce nothing.
+  // 3 = G (128 threads/row), 4 = W (one warp/row); rows with w == 0 produce nothing.
   auto thr = [&](const BinCfg &f) -> uint32_t { return f.dense ? 0xffffffffu : (uint32_t)f.cap; };
   uint32_t tL = thr(cfgL);
-  uint32_t tC = std::min<uint32_t>(thr(cfgC), 10922u);
-  uint32_t tWb = warp_ok ? std::min<uint32_t>(thr(cfgWb), 1365u) : 0u;
-  uint32_t tWa = warp_ok ? std::min<uint32_t>(thr(cfgWa), 340u) : 0u;
+  uint32_t tC = std::min<uint32_t>(thr(cfgC), 8192u);
+  uint32_t tWb = std::min<uint32_t>(thr(cfgG), 2048u);
+  uint32_t tWa = warp_ok ? std::min<uint32_t>(thr(cfgW), 256u) : 0u;
   if (tC > tL) tC = tL;
   if (tWb > tC) tWb = tC;
   if (tWa > tWb) tWa = tWb;
@@ -512,15 +517,18 @@ static int run_indicator(cco_ctx *c, Arena &ar, const uint32_t *at_ptr, const in
   a.emit_all = emit_all ? 1 : 0;
   CK(cudaEventRecord(c->ev[4], s));
   if (n_my > 0) {
-    BinCfg *cfgs[kBins] = {&cfgL, &cfgL, &cfgC, &cfgWb, &cfgWa};
+    BinCfg *cfgs[kBins] = {&cfgL, &cfgL, &cfgC, &cfgG, &cfgW};
     for (int b = 0; b < kBins; ++b) {
       if (b == 0 && cfgL.dense) continue;                 // dense L takes every large row in bin 1
-      if ((b == 3 || b == 4) && !warp_ok) continue;       // large top_k: the 256-thread kernel takes the small rows too
+      if (b == 4 && !warp_ok) continue;                   // large top_k: the 128-thread kernel takes the smallest rows too
       RowArgs ab = a;
       ab.bin = b;
       ab.slots = cfgs[b]->slots;
       ab.cap = cfgs[b]->cap;
       ab.cbuf = cfgs[b]->cbuf;
+      ab.caux = cfgs[b]->caux;
+      ab.keep_max = cfgs[b]->keep_max;
+      ab.final_max = cfgs[b]->final_max;
       ab.group_smem_bytes = (int32_t)cfgs[b]->region;
       CKR(launch_rows(c, ab, *cfgs[b]));
     }

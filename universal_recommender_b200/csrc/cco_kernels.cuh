@@ -43,6 +43,9 @@ struct RowArgs {
   int32_t slots;       // hash/dense table words in shared memory
   int32_t cap;         // max distinct keys per pass for hashed rows (load-factor bound)
   int32_t cbuf;        // candidate buffer entries per group (power of two, >= top_k + GROUP)
+  int32_t caux;        // scratch entries for the out-of-place compaction of the radix select (0 for warps)
+  int32_t keep_max;    // M: a prune keeps between top_k and max(M, top_k) candidates
+  int32_t final_max;   // the final sort runs on at most this many candidates (next_pow2(top_k))
   int32_t group_smem_bytes;  // shared memory of one group (multiple of 16)
   const struct ColTerm *col_terms;  // per column of B': {columnEntropy, colB}
   // outputs, strided
@@ -326,8 +329,11 @@ __global__ void k_col_terms(int32_t n_cols, const int32_t *__restrict__ marg, lo
 // (key << count_bits | count), multi-pass over hash partitions when the row's distinct-cell bound
 // exceeds the table capacity.  Nothing of A'^T B' is ever written to HBM except the kept top-k.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool cand_better(unsigned long long ka, uint32_t ca, unsigned long long kb, uint32_t cb) {
-  return ka > kb || (ka == kb && ca < cb);
+// candidate entry, 16 bytes so that the sort moves it with one LDS.128 / STS.128:
+//   x,y = low/high word of the fp64 LLR bit pattern (positive doubles order like unsigned integers),
+//   z = column, w = k11
+__device__ __forceinline__ bool cand_better(const uint4 &p, const uint4 &q) {
+  return p.y > q.y || (p.y == q.y && (p.x > q.x || (p.x == q.x && p.z < q.z)));
 }
 
 template <int GROUP>
@@ -337,33 +343,150 @@ __device__ __forceinline__ void group_sync() {
 
 // bitonic sort of the candidate buffer, best first; pads [n, n2) with key 0 (never valid: LLR > 0)
 template <int GROUP>
-__device__ void sort_candidates(unsigned long long *ckey, uint32_t *ccol, uint32_t *ccnt, int n, int gtid) {
+__device__ void sort_candidates(uint4 *tk, int n, int gtid) {
   int n2 = 1;
   while (n2 < n) n2 <<= 1;
-  for (int i = n + gtid; i < n2; i += GROUP) { ckey[i] = 0ULL; ccol[i] = 0xffffffffu; ccnt[i] = 0; }
+  for (int i = n + gtid; i < n2; i += GROUP) tk[i] = make_uint4(0u, 0u, 0xffffffffu, 0u);
   group_sync<GROUP>();
   for (int k2 = 2; k2 <= n2; k2 <<= 1) {
     for (int j = k2 >> 1; j > 0; j >>= 1) {
       for (int t = gtid; t < (n2 >> 1); t += GROUP) {
-        // t-th compare-exchange pair of this step
-        int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-        int p = i | j;
-        bool up = (i & k2) == 0;
-        unsigned long long ki = ckey[i], kp = ckey[p];
-        uint32_t ci = ccol[i], cp = ccol[p];
-        bool swap = up ? cand_better(kp, cp, ki, ci) : cand_better(ki, ci, kp, cp);
-        if (swap) {
-          ckey[i] = kp; ckey[p] = ki;
-          ccol[i] = cp; ccol[p] = ci;
-          uint32_t tmp = ccnt[i]; ccnt[i] = ccnt[p]; ccnt[p] = tmp;
-        }
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int p = i | j;
+        const bool up = (i & k2) == 0;
+        const uint4 ei = tk[i], ep = tk[p];
+        const bool swap = up ? cand_better(ep, ei) : cand_better(ei, ep);
+        if (swap) { tk[i] = ep; tk[p] = ei; }
       }
       group_sync<GROUP>();
     }
   }
 }
 
+// ---- candidate reduction: MSB-first 8-bit radix select on the composite key (llr hi, llr lo, ~col) ----------
+// Keeps every candidate >= a threshold T chosen so that  top_k <= kept <= max(M, top_k)  (exactly top_k when the
+// key is fully resolved; keys are unique because columns are).  Cost: a few histogram passes over the buffer
+// instead of a full sort.  Returns the kept count; the threshold entry goes to thr (same layout as a candidate).
+__device__ __forceinline__ uint32_t cand_word(const uint4 &e, int wi) { return wi == 0 ? e.y : (wi == 1 ? e.x : ~e.z); }
+
+template <int GROUP>
+__device__ int reduce_candidates(uint4 *tk, uint4 *aux, int n, int k, int M, int *hist, int *ctrl, int gtid) {
+  // ctrl[16..18] = prefix words, ctrl[24] = D, ctrl[25] = c_gt, ctrl[26] = c_D, ctrl[27] = output cursor
+  volatile int *vc = ctrl;
+  uint32_t pre0 = 0u, pre1 = 0u, pre2 = 0u;
+  int nb = 0, above = 0, kept = n;
+  while (true) {
+    for (int i = gtid; i < 256; i += GROUP) hist[i] = 0;
+    group_sync<GROUP>();
+    const int wi = nb >> 5, sh = 24 - (nb & 31);
+    for (int i = gtid; i < n; i += GROUP) {
+      const uint4 e = tk[i];
+      const uint32_t w0 = e.y, w1 = e.x, w2 = ~e.z;
+      bool match;
+      if (nb == 0) match = true;
+      else if (nb < 32) match = (w0 >> (32 - nb)) == (pre0 >> (32 - nb));
+      else if (nb == 32) match = w0 == pre0;
+      else if (nb < 64) match = w0 == pre0 && (w1 >> (64 - nb)) == (pre1 >> (64 - nb));
+      else if (nb == 64) match = w0 == pre0 && w1 == pre1;
+      else match = w0 == pre0 && w1 == pre1 && (w2 >> (96 - nb)) == (pre2 >> (96 - nb));
+      if (match) atomicAdd(&hist[(cand_word(e, wi) >> sh) & 255u], 1);
+    }
+    group_sync<GROUP>();
+    if (gtid < 32) {
+      // lane l owns digits 255-8l .. 248-8l (descending); find the digit holding the (k-above)-th best
+      int c[8], ssum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { c[j] = hist[255 - 8 * gtid - j]; ssum += c[j]; }
+      int incl = ssum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (gtid >= d) incl += v;
+      }
+      const int excl = incl - ssum, need = k - above;
+      if (excl < need && need <= incl) {
+        int run = excl;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (run < need && run + c[j] >= need) { ctrl[24] = 255 - 8 * gtid - j; ctrl[25] = run; ctrl[26] = c[j]; }
+          run += c[j];
+        }
+      }
+    }
+    group_sync<GROUP>();
+    const int D = vc[24], c_gt = vc[25], c_d = vc[26];
+    if (wi == 0) pre0 |= (uint32_t)D << sh; else if (wi == 1) pre1 |= (uint32_t)D << sh; else pre2 |= (uint32_t)D << sh;
+    nb += 8;
+    kept = above + c_gt + c_d;
+    if (kept <= M || nb == 96) break;
+    above += c_gt;
+    group_sync<GROUP>();
+  }
+  // keep e iff key(e) >= prefix (low bits zero)
+  if (gtid == 0) ctrl[27] = 0;
+  group_sync<GROUP>();
+  if (GROUP == 32) {
+    // single warp: in-place batch compaction (reads of a batch complete before its writes)
+    int w = 0;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+      const int i = i0 + gtid;
+      uint4 e = make_uint4(0u, 0u, 0u, 0u);
+      bool keep = false;
+      if (i < n) {
+        e = tk[i];
+        const uint32_t w0 = e.y, w1 = e.x, w2 = ~e.z;
+        keep = w0 > pre0 || (w0 == pre0 && (w1 > pre1 || (w1 == pre1 && w2 >= pre2)));
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      __syncwarp();
+      if (keep) tk[w + __popc(m & ((1u << gtid) - 1u))] = e;
+      w += __popc(m);
+      __syncwarp();
+    }
+  } else {
+    for (int i = gtid; i < n; i += GROUP) {
+      const uint4 e = tk[i];
+      const uint32_t w0 = e.y, w1 = e.x, w2 = ~e.z;
+      const bool keep = w0 > pre0 || (w0 == pre0 && (w1 > pre1 || (w1 == pre1 && w2 >= pre2)));
+      if (keep) aux[atomicAdd(&ctrl[27], 1)] = e;
+    }
+    group_sync<GROUP>();
+    for (int i = gtid; i < kept; i += GROUP) tk[i] = aux[i];
+  }
+  if (gtid == 0) {
+    ctrl[0] = kept;
+    ctrl[4] = (int)pre1; ctrl[5] = (int)pre0; ctrl[6] = (int)~pre2; ctrl[7] = 0;  // threshold as a candidate entry
+    ctrl[1] = 1;
+  }
+  group_sync<GROUP>();
+  return kept;
+}
+
 constexpr int kX12N = 31;  // x12tab[j] = xLogX(ra - j) for j < 31; x12tab[31] = xLogX(N - ra)
+
+template <int GROUP, bool DENSE>
+__device__ __forceinline__ void accumulate(uint32_t *table, uint32_t tsize, uint32_t b, int cbits, uint32_t n_pass,
+                                           uint32_t pass, int *err_flag) {
+  if (DENSE) {
+    atomicAdd(&table[b], 1u);
+    return;
+  }
+  if (n_pass > 1 && ((b * 0x85ebca6bu) >> 12) % n_pass != pass) return;
+  uint32_t slot = __umulhi(b * 0x9e3779b1u, tsize);
+  const uint32_t want = b << cbits;
+  uint32_t probes = 0;
+  while (true) {
+    const uint32_t w = *reinterpret_cast<volatile uint32_t *>(&table[slot]);
+    if ((w >> cbits) == b && w != kEmpty) { atomicAdd(&table[slot], 1u); return; }
+    if (w == kEmpty) {
+      const uint32_t old = atomicCAS(&table[slot], kEmpty, want | 1u);
+      if (old == kEmpty) return;
+      if ((old >> cbits) == b) { atomicAdd(&table[slot], 1u); return; }
+    }
+    slot = (slot + 1 == tsize) ? 0 : slot + 1;
+    if (++probes > tsize) { atomicOr(err_flag, 1); return; }
+  }
+}
 
 template <int GROUP, bool DENSE>
 __global__ void __launch_bounds__(GROUP == 32 ? 256 : GROUP) k_rows(const RowArgs a) {
@@ -374,20 +497,19 @@ __global__ void __launch_bounds__(GROUP == 32 ? 256 : GROUP) k_rows(const RowArg
   const int tid = threadIdx.x, lane = tid & 31;
   const int gid = tid / GROUP, gtid = tid % GROUP, gw = gtid >> 5;
   unsigned char *base = smem_raw + (size_t)gid * a.group_smem_bytes;
-  unsigned long long *tk_key = reinterpret_cast<unsigned long long *>(base);
-  uint32_t *tk_col = reinterpret_cast<uint32_t *>(tk_key + a.cbuf);
-  uint32_t *tk_cnt = tk_col + a.cbuf;
-  double *x12tab = reinterpret_cast<double *>(tk_cnt + a.cbuf);
+  uint4 *tk = reinterpret_cast<uint4 *>(base);
+  uint4 *aux = tk + a.cbuf;                                  // a.caux entries (0 for warp-owned rows)
+  double *x12tab = reinterpret_cast<double *>(aux + a.caux);
   double *x11tab = x12tab + 32;
-  int *ctrl = reinterpret_cast<int *>(x11tab + 32);  // [0] ncand [1] have_thr [2,3] thr_key [4] thr_col [8..8+NW) per-warp list sizes
-  uint32_t *table = reinterpret_cast<uint32_t *>(ctrl + 64);
+  int *ctrl = reinterpret_cast<int *>(x11tab + 32);  // [0] ncand [1] have_thr [4..7] threshold entry [16..27] select state [32..32+NW) per-warp list sizes
+  int *hist = ctrl + 64;                                     // 256 bins of the radix select
+  uint32_t *table = reinterpret_cast<uint32_t *>(hist + 256);
   volatile int *vctrl = ctrl;
 
   const int row_begin = a.bin_bounds[a.bin], row_end = a.bin_bounds[a.bin + 1];
   const bool varargs = (a.flags & CCO_FLAG_ENTROPY_VARARGS) != 0;
   const int cbits = a.count_bits;
   const uint32_t cmask = (1u << cbits) - 1u;
-  const uint32_t slots = (uint32_t)a.slots;
   const int prune_limit = a.cbuf - GROUP;
   const long long N = a.n_users;
   const double xN = xlogx(N);
@@ -398,16 +520,19 @@ __global__ void __launch_bounds__(GROUP == 32 ? 256 : GROUP) k_rows(const RowArg
     const int item = a.rows_sorted[ri];
     const uint32_t u_begin = a.at_ptr[item], u_end = a.at_ptr[item + 1];
     const long long ra = a.marg_a[item];
-    uint32_t n_pass = 1;
+    // table sized to the row: load factor <= 1/2 of the distinct-cell bound D = min(w, n_cols_b)
+    uint32_t n_pass = 1, tsize = (uint32_t)a.n_cols_b;
     if (!DENSE) {
-      uint32_t w = a.row_work[item];
-      uint32_t dbound = w < (uint32_t)a.n_cols_b ? w : (uint32_t)a.n_cols_b;
+      const uint32_t w = a.row_work[item];
+      const uint32_t dbound = w < (uint32_t)a.n_cols_b ? w : (uint32_t)a.n_cols_b;
       n_pass = (dbound + (uint32_t)a.cap - 1u) / (uint32_t)a.cap;
       if (n_pass == 0) n_pass = 1;
+      tsize = n_pass > 1 ? (uint32_t)a.slots : min((uint32_t)a.slots, max(2u * dbound, 64u));
+      tsize = min((uint32_t)a.slots, (tsize + 32u * NW - 1u) / (32u * NW) * (32u * NW));
     }
-    group_sync<GROUP>();  // previous row fully done with smem
+    group_sync<GROUP>();  // previous row fully done with shared memory
     if (gtid < 32) {
-      long long v = (gtid < kX12N) ? ra - gtid : N - ra;
+      const long long v = (gtid < kX12N) ? ra - gtid : N - ra;
       x12tab[gtid] = v >= 0 ? xlogx(v) : 0.0;
     }
     if (gtid == 0) { ctrl[0] = 0; ctrl[1] = 0; }
@@ -415,14 +540,16 @@ __global__ void __launch_bounds__(GROUP == 32 ? 256 : GROUP) k_rows(const RowArg
 
     for (uint32_t pass = 0; pass < n_pass; ++pass) {
       // ---- clear --------------------------------------------------------------------------------------
-      const uint32_t clear_n = DENSE ? (uint32_t)a.n_cols_b : slots;
-      for (uint32_t i = gtid; i < clear_n; i += GROUP) table[i] = DENSE ? 0u : kEmpty;
+      for (uint32_t i = gtid; i < tsize; i += GROUP) table[i] = DENSE ? 0u : kEmpty;
       group_sync<GROUP>();
       // ---- count: each warp takes 32-user chunks; products of a chunk are flattened over the lanes -----
-      for (uint32_t c0 = u_begin + gw * 32; c0 < u_end; c0 += NW * 32) {
+      // users are dealt to the group's warps in equal chunks of <= 32 so short rows still use every warp
+      const uint32_t deg = u_end - u_begin;
+      const uint32_t per = NW == 1 ? 32u : min(32u, max(1u, (deg + NW - 1) / NW));
+      for (uint32_t c0 = u_begin + gw * per; c0 < u_end; c0 += NW * per) {
         const uint32_t i = c0 + lane;
         uint32_t s = 0, len = 0;
-        if (i < u_end) {
+        if (lane < per && i < u_end) {
           const int32_t u = a.at_users[i];
           s = a.b_ptr[u];
           len = a.b_ptr[u + 1] - s;
@@ -430,52 +557,38 @@ __global__ void __launch_bounds__(GROUP == 32 ? 256 : GROUP) k_rows(const RowArg
         uint32_t off = len;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-          uint32_t v = __shfl_up_sync(0xffffffffu, off, d);
+          const uint32_t v = __shfl_up_sync(0xffffffffu, off, d);
           if (lane >= d) off += v;
         }
         const uint32_t total = __shfl_sync(0xffffffffu, off, 31);
         off -= len;  // exclusive
-        for (uint32_t p0 = 0; p0 < total; p0 += 32) {
-          const uint32_t p = p0 + lane;
-          int j = 0;
+        for (uint32_t p0 = 0; p0 < total; p0 += 64) {
+          // two products per lane per trip (two independent gathers in flight)
+          uint32_t bb[2];
+          bool act[2];
 #pragma unroll
-          for (int st = 16; st > 0; st >>= 1) {
-            const int c = j + st;
-            const uint32_t v = __shfl_sync(0xffffffffu, off, c);
-            if (v <= p) j = c;
-          }
-          const uint32_t sj = __shfl_sync(0xffffffffu, s, j), oj = __shfl_sync(0xffffffffu, off, j);
-          if (p < total) {
-            const uint32_t b = (uint32_t)a.b_col[sj + (p - oj)];
-            if (DENSE) {
-              atomicAdd(&table[b], 1u);
-            } else {
-              const uint32_t h = hash32(b);
-              if (n_pass == 1 || (h % n_pass) == pass) {
-                uint32_t slot = __umulhi(h * 0x9e3779b1u, slots);
-                const uint32_t want = b << cbits;
-                uint32_t probes = 0;
-                while (true) {
-                  uint32_t w = *reinterpret_cast<volatile uint32_t *>(&table[slot]);
-                  if ((w >> cbits) == b && w != kEmpty) { atomicAdd(&table[slot], 1u); break; }
-                  if (w == kEmpty) {
-                    uint32_t old = atomicCAS(&table[slot], kEmpty, want | 1u);
-                    if (old == kEmpty) break;
-                    if ((old >> cbits) == b) { atomicAdd(&table[slot], 1u); break; }
-                  }
-                  slot = (slot + 1 == slots) ? 0 : slot + 1;
-                  if (++probes > slots) { atomicOr(a.err_flag, 1); break; }
-                }
-              }
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t p = p0 + h * 32 + lane;
+            int j = 0;
+#pragma unroll
+            for (int st = 16; st > 0; st >>= 1) {
+              const int c = j + st;
+              const uint32_t v = __shfl_sync(0xffffffffu, off, c);
+              if (v <= p) j = c;
             }
+            const uint32_t sj = __shfl_sync(0xffffffffu, s, j), oj = __shfl_sync(0xffffffffu, off, j);
+            act[h] = p < total;
+            bb[h] = act[h] ? (uint32_t)a.b_col[sj + (p - oj)] : 0u;
           }
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            if (act[h]) accumulate<GROUP, DENSE>(table, tsize, bb[h], cbits, n_pass, pass, a.err_flag);
         }
       }
       group_sync<GROUP>();
       // ---- compact: each warp packs the occupied words of its own table segment, in place ----------------
-      const uint32_t scan_n = DENSE ? (uint32_t)a.n_cols_b : slots;
-      const uint32_t seg = (((scan_n + NW - 1) / NW) + 31u) & ~31u;
-      const uint32_t seg_lo = min((uint32_t)gw * seg, scan_n), seg_hi = min(seg_lo + seg, scan_n);
+      const uint32_t seg = (((tsize + NW - 1) / NW) + 31u) & ~31u;
+      const uint32_t seg_lo = min((uint32_t)gw * seg, tsize), seg_hi = min(seg_lo + seg, tsize);
       uint32_t n_mine = 0;
       for (uint32_t pos = seg_lo; pos < seg_hi; pos += 32) {
         const uint32_t idx = pos + lane;
@@ -489,12 +602,12 @@ __global__ void __launch_bounds__(GROUP == 32 ? 256 : GROUP) k_rows(const RowArg
         n_mine += __popc(m);
         __syncwarp();
       }
-      if (lane == 0) { distinct_local += n_mine; if (NW > 1) ctrl[8 + gw] = (int)n_mine; }
+      if (lane == 0) { distinct_local += n_mine; if (NW > 1) ctrl[32 + gw] = (int)n_mine; }
       int iters = (int)((n_mine + 31) / 32);
       if (NW > 1) {
         group_sync<GROUP>();
         iters = 0;
-        for (int w2 = 0; w2 < NW; ++w2) iters = max(iters, (vctrl[8 + w2] + 31) / 32);
+        for (int w2 = 0; w2 < NW; ++w2) iters = max(iters, (vctrl[32 + w2] + 31) / 32);
       }
       if (a.emit_all) {
         // debug: every non-zero cell of the row (col, count), unordered
@@ -521,12 +634,10 @@ __global__ void __launch_bounds__(GROUP == 32 ? 256 : GROUP) k_rows(const RowArg
       for (int it = 0; it < iters; ++it) {
         const uint32_t q = (uint32_t)it * 32 + lane;
         bool pass_ok = false;
-        unsigned long long key = 0;
-        uint32_t b = 0, k11 = 0;
+        uint4 e = make_uint4(0u, 0u, 0u, 0u);
         if (q < n_mine) {
           const uint32_t word = table[seg_lo + q];
-          b = word >> cbits;
-          k11 = word & cmask;
+          const uint32_t b = word >> cbits, k11 = word & cmask;
           if (!(a.self && (int)b == item)) {
             const ColTerm ct = a.col_terms[b];
             const long long cb = ct.cb;
@@ -539,13 +650,14 @@ __global__ void __launch_bounds__(GROUP == 32 ? 256 : GROUP) k_rows(const RowArg
               mat_e = __dsub_rn(xN, __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(0.0, x11), x12), x21), x22));
             else
               mat_e = __dsub_rn(__dsub_rn(__dsub_rn(__dsub_rn(xN, x11), x12), x21), x22);
-            const double s = __dadd_rn(row_e, ct.col_e);
-            const double v = (s < mat_e) ? 0.0 : __dmul_rn(2.0, __dsub_rn(s, mat_e));
+            const double sre = __dadd_rn(row_e, ct.col_e);
+            const double v = (sre < mat_e) ? 0.0 : __dmul_rn(2.0, __dsub_rn(sre, mat_e));
             pass_ok = v > 0.0 && (!a.has_min_llr || v >= a.min_llr);
-            key = (unsigned long long)__double_as_longlong(v);
+            const unsigned long long key = (unsigned long long)__double_as_longlong(v);
+            e = make_uint4((uint32_t)key, (uint32_t)(key >> 32), b, k11);
             if (pass_ok && vctrl[1]) {
-              const unsigned long long tk = *reinterpret_cast<volatile unsigned long long *>(&ctrl[2]);
-              pass_ok = cand_better(key, b, tk, (uint32_t)vctrl[4]);
+              const uint4 thr = make_uint4((uint32_t)vctrl[4], (uint32_t)vctrl[5], (uint32_t)vctrl[6], (uint32_t)vctrl[7]);
+              pass_ok = !cand_better(thr, e);
             }
           }
         }
@@ -554,25 +666,11 @@ __global__ void __launch_bounds__(GROUP == 32 ? 256 : GROUP) k_rows(const RowArg
           int basepos = 0;
           if (lane == 0) basepos = atomicAdd(&ctrl[0], __popc(m));
           basepos = __shfl_sync(0xffffffffu, basepos, 0);
-          if (pass_ok) {
-            const int pos = basepos + __popc(m & ((1u << lane) - 1u));
-            tk_key[pos] = key; tk_col[pos] = b; tk_cnt[pos] = k11;
-          }
+          if (pass_ok) tk[basepos + __popc(m & ((1u << lane) - 1u))] = e;
         }
         group_sync<GROUP>();
         const int n = vctrl[0];
-        if (n > prune_limit) {
-          sort_candidates<GROUP>(tk_key, tk_col, tk_cnt, n, gtid);
-          if (gtid == 0) {
-            ctrl[0] = n < a.top_k ? n : a.top_k;
-            if (n >= a.top_k) {
-              *reinterpret_cast<unsigned long long *>(&ctrl[2]) = tk_key[a.top_k - 1];
-              ctrl[4] = (int)tk_col[a.top_k - 1];
-              ctrl[1] = 1;
-            }
-          }
-          group_sync<GROUP>();
-        }
+        if (n > prune_limit) reduce_candidates<GROUP>(tk, aux, n, a.top_k, a.keep_max, hist, ctrl, gtid);
       }
       group_sync<GROUP>();
     }
@@ -580,15 +678,17 @@ __global__ void __launch_bounds__(GROUP == 32 ? 256 : GROUP) k_rows(const RowArg
     if (a.emit_all) {
       if (gtid == 0) a.out_len[item] = emitted;
     } else {
-      const int n = vctrl[0];
+      int n = vctrl[0];
       if (n > 0) {
-        sort_candidates<GROUP>(tk_key, tk_col, tk_cnt, n, gtid);
+        if (n > a.final_max) n = reduce_candidates<GROUP>(tk, aux, n, a.top_k, a.final_max, hist, ctrl, gtid);
+        sort_candidates<GROUP>(tk, n, gtid);
         const int keep = n < a.top_k ? n : a.top_k;
         for (int i = gtid; i < keep; i += GROUP) {
           const size_t o = (size_t)item * a.out_stride + i;
-          a.out_col[o] = (int32_t)tk_col[i];
-          a.out_llr[o] = __longlong_as_double((long long)tk_key[i]);
-          a.out_cnt[o] = (int32_t)tk_cnt[i];
+          const uint4 e = tk[i];
+          a.out_col[o] = (int32_t)e.z;
+          a.out_llr[o] = __longlong_as_double((long long)(((unsigned long long)e.y << 32) | e.x));
+          a.out_cnt[o] = (int32_t)e.w;
         }
         if (gtid == 0) a.out_len[item] = keep;
       } else if (gtid == 0) {
