@@ -1,0 +1,59 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/cco_b200.h declares; without a GPU
+every compute entry fails loudly (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "cco_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(cco_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_header_and_binding_agree():
+    from universal_recommender_b200 import _native
+    assert declared_symbols() == sorted(_native.EXPORTS)
+
+
+def test_library_exports_every_declared_symbol():
+    from universal_recommender_b200 import _native
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    for name in declared_symbols():
+        assert hasattr(lib, name), f"{name} declared in include/cco_b200.h but not exported"
+    assert lib.cco_abi_version() == 1
+
+
+def test_status_strings():
+    from universal_recommender_b200 import _native
+    L = _native.lib()
+    assert L.cco_status_string(0) == b"ok"
+    assert L.cco_status_string(_native.E_SHAPE_MISMATCH) == b"shape mismatch"
+
+
+def test_no_cpu_fallback_without_gpu():
+    """On the CPU box cco_create must fail with CCO_E_CUDA -- the product path never routes through a CPU path."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("this check is for the CPU-only box")
+    import universal_recommender_b200 as ur
+    with pytest.raises(ur.CcoError) as e:
+        ur.CcoContext(device=0)
+    assert e.value.status == -2 and "no CPU fallback" in str(e.value)
+
+
+def test_product_package_never_imports_the_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py may touch oracle/."""
+    pkg = os.path.join(ROOT, "universal_recommender_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.lower() or f in ("cco_kernels.cuh",), f"{f} mentions the oracle"
+    k = open(os.path.join(pkg, "csrc", "cco_kernels.cuh")).read()
+    assert "#include" not in "".join(l for l in k.splitlines() if "oracle" in l.lower())

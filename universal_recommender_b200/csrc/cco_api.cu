@@ -99,6 +99,8 @@ struct cco_ctx {
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev[8] = {};
   cudaEvent_t tev[2] = {};
+  cudaStream_t bin_stream[8] = {};
+  cudaEvent_t bin_ev[9] = {};
   std::vector<PinnedBuf> pinned;
   std::mutex mu;
   ncclComm_t comm = nullptr;
@@ -305,29 +307,30 @@ static int next_pow2(int x) {
 }
 
 template <int GROUP>
-static int launch_rows_t(cco_ctx *c, const RowArgs &a, BinCfg &cfg) {
+static int launch_rows_t(cco_ctx *c, const RowArgs &a, BinCfg &cfg, cudaStream_t st) {
   constexpr int CTA = GROUP == 32 ? 256 : GROUP;
   int occ = 1;
   if (cfg.dense) {
     CK(cudaFuncSetAttribute(k_rows<GROUP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_rows<GROUP, true>, CTA, cfg.smem));
-    k_rows<GROUP, true><<<c->sm_count * std::max(occ, 1), CTA, cfg.smem, c->stream>>>(a);
+    k_rows<GROUP, true><<<c->sm_count * std::max(occ, 1), CTA, cfg.smem, st>>>(a);
   } else {
     CK(cudaFuncSetAttribute(k_rows<GROUP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_rows<GROUP, false>, CTA, cfg.smem));
-    k_rows<GROUP, false><<<c->sm_count * std::max(occ, 1), CTA, cfg.smem, c->stream>>>(a);
+    k_rows<GROUP, false><<<c->sm_count * std::max(occ, 1), CTA, cfg.smem, st>>>(a);
   }
   cfg.ctas_per_sm = occ;
   c->launches++;
   CK(cudaGetLastError());
   return CCO_OK;
 }
-static int launch_rows(cco_ctx *c, const RowArgs &a, BinCfg &cfg) {
+static int launch_rows(cco_ctx *c, const RowArgs &a, BinCfg &cfg, cudaStream_t st) {
   switch (cfg.group) {
-    case 1024: return launch_rows_t<1024>(c, a, cfg);
-    case 256: return launch_rows_t<256>(c, a, cfg);
-    case 128: return launch_rows_t<128>(c, a, cfg);
-    case 32: return launch_rows_t<32>(c, a, cfg);
+    case 1024: return launch_rows_t<1024>(c, a, cfg, st);
+    case 512: return launch_rows_t<512>(c, a, cfg, st);
+    case 256: return launch_rows_t<256>(c, a, cfg, st);
+    case 128: return launch_rows_t<128>(c, a, cfg, st);
+    case 32: return launch_rows_t<32>(c, a, cfg, st);
   }
   return set_error(CCO_E_INVALID_ARG, "internal: bad bin config");
 }
@@ -433,7 +436,8 @@ static int run_indicator(cco_ctx *c, Arena &ar, const uint32_t *at_ptr, const in
   const int k_eff = emit_all ? 1 : prm.top_k;
   const bool warp_ok = k_eff + 32 <= 256;  // warp-owned rows keep a 256-entry candidate buffer
   BinCfg cfgL = make_cfg(c, 1024, 1 << 20, k_eff, n_cols_b);
-  BinCfg cfgC = make_cfg(c, 256, 16384, k_eff, n_cols_b);
+  BinCfg cfgD = make_cfg(c, 512, 16384, k_eff, n_cols_b);
+  BinCfg cfgC = make_cfg(c, 256, 8192, k_eff, n_cols_b);
   BinCfg cfgG = make_cfg(c, 128, 4096, k_eff, n_cols_b);
   BinCfg cfgW = make_cfg(c, 32, 512, k_eff, n_cols_b);
   // packed word: key bits must leave room for the largest possible count (= users of the item)
@@ -444,18 +448,13 @@ static int run_indicator(cco_ctx *c, Arena &ar, const uint32_t *at_ptr, const in
     return set_error(CCO_E_UNSUPPORTED,
                      "an item with %d users and %d columns does not fit the packed 32-bit accumulator word "
                      "(key %d bits + count %d bits)", max_marg_a, n_cols_b, key_bits, count_bits);
-  // bins by WORK w (descending thresholds): 0 = multi-pass L, 1 = L (1024 threads/row), 2 = C (256 threads/row),
-  // 3 = G (128 threads/row), 4 = W (one warp/row); rows with w == 0 produce nothing.
+  // bins by WORK w (descending thresholds): 0 = multi-pass L, 1 = L (1024 threads/row), 2 = D (512), 3 = C (256),
+  // 4 = G (128), 5 = W (one warp/row); rows with w == 0 produce nothing.
   auto thr = [&](const BinCfg &f) -> uint32_t { return f.dense ? 0xffffffffu : (uint32_t)f.cap; };
-  uint32_t tL = thr(cfgL);
-  uint32_t tC = std::min<uint32_t>(thr(cfgC), 8192u);
-  uint32_t tWb = std::min<uint32_t>(thr(cfgG), 2048u);
-  uint32_t tWa = warp_ok ? std::min<uint32_t>(thr(cfgW), 256u) : 0u;
-  if (tC > tL) tC = tL;
-  if (tWb > tC) tWb = tC;
-  if (tWa > tWb) tWa = tWb;
-  constexpr int kBins = 5;
-  uint32_t h_thr[kBins] = {tL, tC, tWb, tWa, 0u};
+  constexpr int kBins = 6;
+  uint32_t h_thr[kBins] = {thr(cfgL), std::min<uint32_t>(thr(cfgD), 8192u), std::min<uint32_t>(thr(cfgC), 4096u),
+                           std::min<uint32_t>(thr(cfgG), 2048u), warp_ok ? std::min<uint32_t>(thr(cfgW), 256u) : 0u, 0u};
+  for (int b = 1; b < kBins; ++b) h_thr[b] = std::min(h_thr[b], h_thr[b - 1]);
   uint32_t *d_thr;
   int32_t *d_bounds;
   CKR(ar.alloc(&d_thr, kBins));
@@ -517,10 +516,12 @@ static int run_indicator(cco_ctx *c, Arena &ar, const uint32_t *at_ptr, const in
   a.emit_all = emit_all ? 1 : 0;
   CK(cudaEventRecord(c->ev[4], s));
   if (n_my > 0) {
-    BinCfg *cfgs[kBins] = {&cfgL, &cfgL, &cfgC, &cfgG, &cfgW};
+    BinCfg *cfgs[kBins] = {&cfgL, &cfgL, &cfgD, &cfgC, &cfgG, &cfgW};
+    // the bins touch disjoint rows: run them concurrently (tails of one bin overlap the bulk of another)
+    CK(cudaEventRecord(c->bin_ev[8], s));
     for (int b = 0; b < kBins; ++b) {
       if (b == 0 && cfgL.dense) continue;                 // dense L takes every large row in bin 1
-      if (b == 4 && !warp_ok) continue;                   // large top_k: the 128-thread kernel takes the smallest rows too
+      if (b == 5 && !warp_ok) continue;                   // large top_k: the 128-thread kernel takes the smallest rows too
       RowArgs ab = a;
       ab.bin = b;
       ab.slots = cfgs[b]->slots;
@@ -530,7 +531,10 @@ static int run_indicator(cco_ctx *c, Arena &ar, const uint32_t *at_ptr, const in
       ab.keep_max = cfgs[b]->keep_max;
       ab.final_max = cfgs[b]->final_max;
       ab.group_smem_bytes = (int32_t)cfgs[b]->region;
-      CKR(launch_rows(c, ab, *cfgs[b]));
+      CK(cudaStreamWaitEvent(c->bin_stream[b], c->bin_ev[8], 0));
+      CKR(launch_rows(c, ab, *cfgs[b], c->bin_stream[b]));
+      CK(cudaEventRecord(c->bin_ev[b], c->bin_stream[b]));
+      CK(cudaStreamWaitEvent(s, c->bin_ev[b], 0));
     }
   }
   CK(cudaEventRecord(c->ev[5], s));
@@ -890,6 +894,8 @@ int cco_create(const cco_config_t *cfg, cco_ctx_t **out) {
   CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   for (auto &ev : c->ev) CK(cudaEventCreate(&ev));
   for (auto &ev : c->tev) CK(cudaEventCreate(&ev));
+  for (auto &st : c->bin_stream) CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  for (auto &ev : c->bin_ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   cudaMemPool_t pool;
   CK(cudaDeviceGetDefaultMemPool(&pool, cfg->device));
   uint64_t thr = UINT64_MAX;
@@ -925,6 +931,10 @@ int cco_destroy(cco_ctx_t *c) {
   for (auto &ev : c->ev)
     if (ev) cudaEventDestroy(ev);
   for (auto &ev : c->tev)
+    if (ev) cudaEventDestroy(ev);
+  for (auto &st : c->bin_stream)
+    if (st) cudaStreamDestroy(st);
+  for (auto &ev : c->bin_ev)
     if (ev) cudaEventDestroy(ev);
   cudaStreamDestroy(c->stream);
   cudaStreamDestroy(c->copy_stream);

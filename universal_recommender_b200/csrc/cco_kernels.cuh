@@ -670,7 +670,15 @@ __global__ void __launch_bounds__(GROUP == 32 ? 256 : GROUP) k_rows(const RowArg
         }
         group_sync<GROUP>();
         const int n = vctrl[0];
-        if (n > prune_limit) reduce_candidates<GROUP>(tk, aux, n, a.top_k, a.keep_max, hist, ctrl, gtid);
+        if (n > prune_limit) {
+          if (GROUP > 32 && n <= 512) {
+            // small buffer: one warp runs the whole select (no CTA barriers inside), the others wait once
+            if (gw == 0) reduce_candidates<32>(tk, aux, n, a.top_k, a.keep_max, hist, ctrl, lane);
+            group_sync<GROUP>();
+          } else {
+            reduce_candidates<GROUP>(tk, aux, n, a.top_k, a.keep_max, hist, ctrl, gtid);
+          }
+        }
       }
       group_sync<GROUP>();
     }
@@ -680,8 +688,19 @@ __global__ void __launch_bounds__(GROUP == 32 ? 256 : GROUP) k_rows(const RowArg
     } else {
       int n = vctrl[0];
       if (n > 0) {
-        if (n > a.final_max) n = reduce_candidates<GROUP>(tk, aux, n, a.top_k, a.final_max, hist, ctrl, gtid);
-        sort_candidates<GROUP>(tk, n, gtid);
+        if (GROUP > 32 && n <= 512) {
+          if (gw == 0) {
+            int m = n;
+            if (m > a.final_max) m = reduce_candidates<32>(tk, aux, m, a.top_k, a.final_max, hist, ctrl, lane);
+            sort_candidates<32>(tk, m, lane);
+            if (lane == 0) ctrl[0] = m;
+          }
+          group_sync<GROUP>();
+          n = vctrl[0];
+        } else {
+          if (n > a.final_max) n = reduce_candidates<GROUP>(tk, aux, n, a.top_k, a.final_max, hist, ctrl, gtid);
+          sort_candidates<GROUP>(tk, n, gtid);
+        }
         const int keep = n < a.top_k ? n : a.top_k;
         for (int i = gtid; i < keep; i += GROUP) {
           const size_t o = (size_t)item * a.out_stride + i;
