@@ -310,15 +310,10 @@ template <int GROUP>
 static int launch_rows_t(cco_ctx *c, const RowArgs &a, BinCfg &cfg, cudaStream_t st) {
   constexpr int CTA = GROUP == 32 ? 256 : GROUP;
   int occ = 1;
-  if (cfg.dense) {
-    CK(cudaFuncSetAttribute(k_rows<GROUP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_rows<GROUP, true>, CTA, cfg.smem));
-    k_rows<GROUP, true><<<c->sm_count * std::max(occ, 1), CTA, cfg.smem, st>>>(a);
-  } else {
-    CK(cudaFuncSetAttribute(k_rows<GROUP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_rows<GROUP, false>, CTA, cfg.smem));
-    k_rows<GROUP, false><<<c->sm_count * std::max(occ, 1), CTA, cfg.smem, st>>>(a);
-  }
+  void (*kern)(const RowArgs) = cfg.dense ? k_rows<GROUP, true> : k_rows<GROUP, false>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, CTA, cfg.smem));
+  kern<<<c->sm_count * std::max(occ, 1), CTA, cfg.smem, st>>>(a);
   cfg.ctas_per_sm = occ;
   c->launches++;
   CK(cudaGetLastError());
@@ -339,11 +334,11 @@ static BinCfg make_cfg(cco_ctx *c, int group, int want_slots, int top_k, int n_c
   BinCfg f;
   const int groups = group == 32 ? 8 : 1;
   f.group = group;
-  f.cbuf = next_pow2(top_k + std::max(group, 128) + (group == 32 ? 64 : 0));
   f.final_max = next_pow2(top_k);
+  f.cbuf = next_pow2(top_k + std::max(group, 128) + (group == 32 ? 64 : 0));
   f.keep_max = std::max(f.final_max, (f.cbuf - group) / 2);
   f.caux = group == 32 ? 0 : f.keep_max;
-  size_t fixed = (size_t)(f.cbuf + f.caux) * 16 + 3 * 256 + 1024;
+  size_t fixed = (size_t)(f.cbuf + f.caux) * 16 + 2 * 256 + 512 + 1024;  // candidates, x12/x11 tables, ctrl, histogram
   size_t avail = (c->smem_optin - 1024) / groups;  // slack for static shared memory
   int max_slots = (int)((avail - fixed) / 4) & ~1023;
   f.slots = std::min(want_slots, max_slots);

@@ -462,6 +462,7 @@ __device__ int reduce_candidates(uint4 *tk, uint4 *aux, int n, int k, int M, int
   return kept;
 }
 
+constexpr int kDomLevels = 15;  // dominance filter keeps cfail[1..15] in ctrl[41..55]
 constexpr int kX12N = 31;  // x12tab[j] = xLogX(ra - j) for j < 31; x12tab[31] = xLogX(N - ra)
 
 template <int GROUP, bool DENSE>
@@ -501,8 +502,8 @@ __global__ void __launch_bounds__(GROUP == 32 ? 256 : GROUP) k_rows(const RowArg
   uint4 *aux = tk + a.cbuf;                                  // a.caux entries (0 for warp-owned rows)
   double *x12tab = reinterpret_cast<double *>(aux + a.caux);
   double *x11tab = x12tab + 32;
-  int *ctrl = reinterpret_cast<int *>(x11tab + 32);  // [0] ncand [1] have_thr [4..7] threshold entry [16..27] select state [32..32+NW) per-warp list sizes
-  int *hist = ctrl + 64;                                     // 256 bins of the radix select
+  int *ctrl = reinterpret_cast<int *>(x11tab + 32);  // [0] ncand [1] have_thr [4..7] threshold entry [16..27] select state [40..55] dominance frontier [64..64+NW) per-warp list sizes
+  int *hist = ctrl + 128;                                     // 256 bins of the radix select
   uint32_t *table = reinterpret_cast<uint32_t *>(hist + 256);
   volatile int *vctrl = ctrl;
 
@@ -536,6 +537,7 @@ __global__ void __launch_bounds__(GROUP == 32 ? 256 : GROUP) k_rows(const RowArg
       x12tab[gtid] = v >= 0 ? xlogx(v) : 0.0;
     }
     if (gtid == 0) { ctrl[0] = 0; ctrl[1] = 0; }
+    if (gtid < 16) ctrl[40 + gtid] = 0x7fffffff;
     int emitted = 0;
 
     for (uint32_t pass = 0; pass < n_pass; ++pass) {
@@ -602,12 +604,12 @@ __global__ void __launch_bounds__(GROUP == 32 ? 256 : GROUP) k_rows(const RowArg
         n_mine += __popc(m);
         __syncwarp();
       }
-      if (lane == 0) { distinct_local += n_mine; if (NW > 1) ctrl[32 + gw] = (int)n_mine; }
+      if (lane == 0) { distinct_local += n_mine; if (NW > 1) ctrl[64 + gw] = (int)n_mine; }
       int iters = (int)((n_mine + 31) / 32);
       if (NW > 1) {
         group_sync<GROUP>();
         iters = 0;
-        for (int w2 = 0; w2 < NW; ++w2) iters = max(iters, (vctrl[32 + w2] + 31) / 32);
+        for (int w2 = 0; w2 < NW; ++w2) iters = max(iters, (vctrl[64 + w2] + 31) / 32);
       }
       if (a.emit_all) {
         // debug: every non-zero cell of the row (col, count), unordered
@@ -641,23 +643,39 @@ __global__ void __launch_bounds__(GROUP == 32 ? 256 : GROUP) k_rows(const RowArg
           if (!(a.self && (int)b == item)) {
             const ColTerm ct = a.col_terms[b];
             const long long cb = ct.cb;
-            const long long k21 = cb - k11, k22 = N - ra - cb + k11;
-            const double x11 = k11 < 32 ? x11tab[k11] : xlogx((long long)k11);
-            const double x12 = k11 < kX12N ? x12tab[k11] : xlogx(ra - k11);
-            const double x21 = xlogx(k21), x22 = xlogx(k22);
-            double mat_e;
-            if (varargs)
-              mat_e = __dsub_rn(xN, __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(0.0, x11), x12), x21), x22));
-            else
-              mat_e = __dsub_rn(__dsub_rn(__dsub_rn(__dsub_rn(xN, x11), x12), x21), x22);
-            const double sre = __dadd_rn(row_e, ct.col_e);
-            const double v = (sre < mat_e) ? 0.0 : __dmul_rn(2.0, __dsub_rn(sre, mat_e));
-            pass_ok = v > 0.0 && (!a.has_min_llr || v >= a.min_llr);
-            const unsigned long long key = (unsigned long long)__double_as_longlong(v);
-            e = make_uint4((uint32_t)key, (uint32_t)(key >> 32), b, k11);
-            if (pass_ok && vctrl[1]) {
-              const uint4 thr = make_uint4((uint32_t)vctrl[4], (uint32_t)vctrl[5], (uint32_t)vctrl[6], (uint32_t)vctrl[7]);
-              pass_ok = !cand_better(thr, e);
+            // Dominance filter (exact, DESIGN.md "dominance"): for fixed rowA and N, on the positively associated side
+            // (rowA*cb < k11*N) the LLR grows with k11 and shrinks with cb.  Every evaluated cell (k, c) that fails
+            // strictly on LLR therefore proves that all cells (k' <= k, c' >= c) fail too; cfail[k'] keeps the
+            // smallest such c seen so far for this row, and those cells skip the fp64 evaluation.
+            const bool pos_side = (unsigned long long)ra * (unsigned long long)cb < (unsigned long long)k11 * (unsigned long long)N;
+            const uint32_t kf = k11 < (uint32_t)kDomLevels ? k11 : (uint32_t)kDomLevels;
+            const bool skip = pos_side && k11 <= (uint32_t)kDomLevels && (int)cb >= vctrl[40 + k11];
+            if (!skip) {
+              const long long k21 = cb - k11, k22 = N - ra - cb + k11;
+              const double x11 = k11 < 32 ? x11tab[k11] : xlogx((long long)k11);
+              const double x12 = k11 < kX12N ? x12tab[k11] : xlogx(ra - k11);
+              const double x21 = xlogx(k21), x22 = xlogx(k22);
+              double mat_e;
+              if (varargs)
+                mat_e = __dsub_rn(xN, __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(0.0, x11), x12), x21), x22));
+              else
+                mat_e = __dsub_rn(__dsub_rn(__dsub_rn(__dsub_rn(xN, x11), x12), x21), x22);
+              const double sre = __dadd_rn(row_e, ct.col_e);
+              const double v = (sre < mat_e) ? 0.0 : __dmul_rn(2.0, __dsub_rn(sre, mat_e));
+              const bool min_ok = !a.has_min_llr || v >= a.min_llr;
+              pass_ok = v > 0.0 && min_ok;
+              // (cells whose LLR rounds to 0 are cancellation noise: they teach nothing)
+              bool strict_fail = v > 0.0 && !min_ok;
+              const unsigned long long key = (unsigned long long)__double_as_longlong(v);
+              e = make_uint4((uint32_t)key, (uint32_t)(key >> 32), b, k11);
+              if (pass_ok && vctrl[1]) {
+                const uint4 thr = make_uint4((uint32_t)vctrl[4], (uint32_t)vctrl[5], (uint32_t)vctrl[6], (uint32_t)vctrl[7]);
+                pass_ok = !cand_better(thr, e);
+                strict_fail = e.y < thr.y || (e.y == thr.y && e.x < thr.x);
+              }
+              if (strict_fail && pos_side) {
+                for (uint32_t kk = kf; kk >= 1 && (int)cb < vctrl[40 + kk]; --kk) atomicMin(&ctrl[40 + kk], (int)cb);
+              }
             }
           }
         }
