@@ -163,6 +163,13 @@ int cco_train_dataset(cco_ctx_t *ctx, const cco_dataset_t *ds, const cco_indicat
                       uint32_t flags, cco_result_t **out);
 int cco_dataset_free(cco_dataset_t *ds);
 
+/*
+ * Pure host helper (no GPU needed): the rank partition cco_train uses.  work_prefix[i] = products of primary items
+ * [0, i) (exclusive prefix, n_items + 1 entries); bounds[r]..bounds[r+1] is rank r's contiguous item range, cut so
+ * that every rank gets an equal share of (products + 1 per row).  Identical on every rank by construction.
+ */
+int cco_partition_rows(const int64_t *work_prefix, int32_t n_items, int32_t world_size, int32_t *bounds);
+
 /* CUDA-event stopwatch on the context's launch stream (what bench.py brackets its timed region with) */
 int cco_timer_start(cco_ctx_t *ctx);
 int cco_timer_stop(cco_ctx_t *ctx, float *ms);

@@ -60,6 +60,7 @@ EXPORTS = [
     "cco_abi_version", "cco_last_error", "cco_status_string", "cco_device_count", "cco_nccl_unique_id",
     "cco_create", "cco_destroy", "cco_host_alloc", "cco_host_free", "cco_train", "cco_cooccurrences_idss",
     "cco_dataset_upload", "cco_train_dataset", "cco_dataset_free", "cco_timer_start", "cco_timer_stop",
+    "cco_partition_rows",
     "cco_result_num_matrices", "cco_result_row_range", "cco_result_matrix", "cco_result_stats", "cco_result_free",
     "cco_debug_cooccurrence", "cco_debug_downsample", "cco_debug_llr", "cco_free",
 ]
@@ -93,6 +94,7 @@ def lib():
     L.cco_dataset_upload.argtypes = [C.c_void_p, C.c_int32, p(CsrT), C.c_uint32, p(C.c_void_p)]
     L.cco_train_dataset.argtypes = [C.c_void_p, C.c_void_p, p(ParamsT), C.c_int32, C.c_uint32, p(C.c_void_p)]
     L.cco_dataset_free.argtypes = [C.c_void_p]
+    L.cco_partition_rows.argtypes = [p(C.c_int64), C.c_int32, C.c_int32, p(C.c_int32)]
     L.cco_timer_start.argtypes = [C.c_void_p]
     L.cco_timer_stop.argtypes = [C.c_void_p, p(C.c_float)]
     L.cco_result_num_matrices.argtypes = [C.c_void_p]

@@ -389,20 +389,10 @@ static int run_indicator(cco_ctx *c, Arena &ar, const uint32_t *at_ptr, const in
     }
     CK(cudaStreamSynchronize(s));
     if (world > 1) {
-      auto cut = [&](int r) -> int32_t {
-        if (r <= 0) return 0;
-        if (r >= world) return n_items_a;
-        // weight = products + a per-row constant so empty-work rows are spread too
-        long long target = (long long)((__int128)(total_work + n_items_a) * r / world);
-        int lo = 0, hi = n_items_a;
-        while (lo < hi) {
-          int mid = (lo + hi) >> 1;
-          if (hp[mid] + mid < target) lo = mid + 1; else hi = mid;
-        }
-        return lo;
-      };
-      row_lo = cut(rank);
-      row_hi = cut(rank + 1);
+      std::vector<int32_t> bounds((size_t)world + 1);
+      CKR(cco_partition_rows(reinterpret_cast<const int64_t *>(hp.data()), n_items_a, world, bounds.data()));
+      row_lo = bounds[rank];
+      row_hi = bounds[rank + 1];
     }
   }
   const int32_t n_my = row_hi - row_lo;
@@ -970,6 +960,24 @@ int cco_cooccurrences_idss(cco_ctx_t *ctx, int32_t n_mats, const cco_csr_t *mats
     q.min_llr = 0.0;
   }
   return cco_train(ctx, n_mats, mats, p.data(), seed, flags, out);
+}
+
+int cco_partition_rows(const int64_t *work_prefix, int32_t n_items, int32_t world_size, int32_t *bounds) {
+  if (!work_prefix || !bounds || n_items < 0 || world_size < 1) return set_error(CCO_E_INVALID_ARG, "bad argument");
+  // weight of row i = its products + 1 (so rows without work are spread too); contiguous ranges of equal weight
+  const long long total = (long long)work_prefix[n_items] + n_items;
+  for (int r = 0; r <= world_size; ++r) {
+    if (r == 0) { bounds[r] = 0; continue; }
+    if (r == world_size) { bounds[r] = n_items; continue; }
+    const long long target = (long long)((__int128)total * r / world_size);
+    int lo = 0, hi = n_items;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if ((long long)work_prefix[mid] + mid < target) lo = mid + 1; else hi = mid;
+    }
+    bounds[r] = lo;
+  }
+  return CCO_OK;
 }
 
 int cco_dataset_upload(cco_ctx_t *ctx, int32_t n_mats, const cco_csr_t *mats, uint32_t flags, cco_dataset_t **out) {
