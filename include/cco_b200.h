@@ -117,6 +117,7 @@ typedef struct {
   int64_t products[16];         /* per indicator: P(A',B') = sum_u degA'(u) * degB'(u), this rank's rows */
   int64_t distinct_cells[16];   /* per indicator: nnz(A'^T B') visited, this rank's rows */
   int64_t out_nnz[16];          /* per indicator: kept cells, this rank's rows */
+  int64_t llr_evaluated[16];    /* per indicator: cells whose fp64 LLR was evaluated (rest: dominance-filtered) */
   float ms_h2d, ms_prepare, ms_cooccurrence, ms_d2h, ms_total; /* CUDA-event times of this call */
   float ms_indicator[16];       /* per indicator: row kernels only */
   int32_t n_kernel_launches;    /* kernels of this library launched by the call */

@@ -14,7 +14,7 @@ for it in range(int(os.environ.get("QC_ITERS", "3"))):
     t0 = time.time(); res = ctx.train_csr(w.mats, w.params, seed=42, flags=ur.FLAG_ASSUME_CANONICAL); dt = time.time() - t0
     st = ctx.last_stats
     print(f"gpu iter {it}: wall {dt*1e3:.1f} ms  total {st.ms_total:.2f} h2d {st.ms_h2d:.2f} prep {st.ms_prepare:.2f} cooc {st.ms_cooccurrence:.2f} rows {['%.3f'%x for x in st.ms_indicator]} launches {st.n_kernel_launches}")
-print("products", st.products, "distinct", st.distinct_cells, "out_nnz", st.out_nnz, "nnz_ds", st.nnz_downsampled)
+print("llr_evaluated", st.llr_evaluated); print("products", st.products, "distinct", st.distinct_cells, "out_nnz", st.out_nnz, "nnz_ds", st.nnz_downsampled)
 if do_oracle:
     mats = [orc.Csr(*m) for m in w.mats]
     t0 = time.time(); ref = orc.train(mats, [orc.Params(*p) for p in w.params], 42); print(f"oracle: {time.time()-t0:.2f}s ({orc.lib().orc_max_threads()} threads)")

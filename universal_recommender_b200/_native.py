@@ -49,7 +49,7 @@ class ConfigT(C.Structure):
 class StatsT(C.Structure):
     _fields_ = [("n_users", C.c_int64), ("nnz_in_total", C.c_int64),
                 ("nnz_downsampled", C.c_int64 * 16), ("products", C.c_int64 * 16),
-                ("distinct_cells", C.c_int64 * 16), ("out_nnz", C.c_int64 * 16),
+                ("distinct_cells", C.c_int64 * 16), ("out_nnz", C.c_int64 * 16), ("llr_evaluated", C.c_int64 * 16),
                 ("ms_h2d", C.c_float), ("ms_prepare", C.c_float), ("ms_cooccurrence", C.c_float),
                 ("ms_d2h", C.c_float), ("ms_total", C.c_float), ("ms_indicator", C.c_float * 16),
                 ("n_kernel_launches", C.c_int32), ("n_mats", C.c_int32)]

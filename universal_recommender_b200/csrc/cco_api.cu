@@ -338,7 +338,7 @@ static BinCfg make_cfg(cco_ctx *c, int group, int want_slots, int top_k, int n_c
   f.cbuf = next_pow2(top_k + std::max(group, 128) + (group == 32 ? 64 : 0));
   f.keep_max = std::max(f.final_max, (f.cbuf - group) / 2);
   f.caux = group == 32 ? 0 : f.keep_max;
-  size_t fixed = (size_t)(f.cbuf + f.caux) * 16 + 2 * 256 + 512 + 1024;  // candidates, x12/x11 tables, ctrl, histogram
+  size_t fixed = (size_t)(f.cbuf + f.caux) * 16 + 2 * 256 + 512 + 1024 + (size_t)(group / 32) * 256;  // candidates, x12/x11 tables, ctrl, histogram, queues
   size_t avail = (c->smem_optin - 1024) / groups;  // slack for static shared memory
   int max_slots = (int)((avail - fixed) / 4) & ~1023;
   f.slots = std::min(want_slots, max_slots);
@@ -353,7 +353,7 @@ static BinCfg make_cfg(cco_ctx *c, int group, int want_slots, int top_k, int n_c
 struct IndicatorOut {
   int64_t row_begin = 0, row_end = 0;
   int64_t nnz = 0;
-  int64_t products = 0, distinct = 0;
+  int64_t products = 0, distinct = 0, evaluated = 0;
 };
 
 // One indicator: rows [row_lo,row_hi) of A'^T B'.  Leaves the packed result in pinned host memory.
@@ -466,10 +466,10 @@ static int run_indicator(cco_ctx *c, Arena &ar, const uint32_t *at_ptr, const in
   CKR(ar.alloc(&o_cnt, cells));
   if (!emit_all) CKR(ar.alloc(&o_llr, cells));
   CKR(ar.alloc(&o_len, n_items_a + 1));
-  CKR(ar.alloc(&d_distinct, 1));
+  CKR(ar.alloc(&d_distinct, 2));
   CKR(ar.alloc(&d_err, 1));
   CK(cudaMemsetAsync(o_len, 0, sizeof(int32_t) * ((size_t)n_items_a + 1), s));
-  CK(cudaMemsetAsync(d_distinct, 0, 8, s));
+  CK(cudaMemsetAsync(d_distinct, 0, 16, s));
   CK(cudaMemsetAsync(d_err, 0, 4, s));
   RowArgs a;
   memset(&a, 0, sizeof a);
@@ -497,6 +497,7 @@ static int run_indicator(cco_ctx *c, Arena &ar, const uint32_t *at_ptr, const in
   a.out_cnt = o_cnt;
   a.out_len = o_len;
   a.stat_distinct = d_distinct;
+  a.stat_evaluated = d_distinct + 1;
   a.err_flag = d_err;
   a.emit_all = emit_all ? 1 : 0;
   CK(cudaEventRecord(c->ev[4], s));
@@ -534,15 +535,16 @@ static int run_indicator(cco_ctx *c, Arena &ar, const uint32_t *at_ptr, const in
   }
   CKR(exclusive_sum_i64(c, ar, len64, out_ptr, (long long)n_my + 1));
   long long total = 0;
-  unsigned long long h_distinct = 0;
+  unsigned long long h_distinct[2] = {0, 0};
   int h_err = 0;
   CK(cudaMemcpyAsync(&total, out_ptr + n_my, 8, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(&h_distinct, d_distinct, 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(h_distinct, d_distinct, 16, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(&h_err, d_err, 4, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   if (h_err) return set_error(CCO_E_CUDA, "internal: shared-memory hash table overflow");
   io->nnz = total;
-  io->distinct = (int64_t)h_distinct;
+  io->distinct = (int64_t)h_distinct[0];
+  io->evaluated = (int64_t)h_distinct[1];
   int32_t *p_col, *p_cnt;
   double *p_llr = nullptr;
   CKR(ar.alloc(&p_col, std::max<long long>(total, 1)));
@@ -783,6 +785,7 @@ static int train_dataset(cco_ctx *c, const cco_dataset *ds, const cco_indicator_
     if (i < 16) {
       st.products[i] = io.products;
       st.distinct_cells[i] = io.distinct;
+      st.llr_evaluated[i] = io.evaluated;
       st.out_nnz[i] = io.nnz;
       st.ms_indicator[i] = ms_rows;
     }

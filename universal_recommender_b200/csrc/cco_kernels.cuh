@@ -55,6 +55,7 @@ struct RowArgs {
   int32_t *out_cnt;
   int32_t *out_len;
   unsigned long long *stat_distinct;
+  unsigned long long *stat_evaluated;  // cells whose fp64 LLR was actually evaluated (after the dominance filter)
   int *err_flag;     // set to 1 if a hash table overflowed (result invalid)
   int32_t emit_all;  // debug: write every non-zero cell (col,count), no LLR/top-k
 };
@@ -504,7 +505,8 @@ __global__ void __launch_bounds__(GROUP == 32 ? 256 : GROUP) k_rows(const RowArg
   double *x11tab = x12tab + 32;
   int *ctrl = reinterpret_cast<int *>(x11tab + 32);  // [0] ncand [1] have_thr [4..7] threshold entry [16..27] select state [40..55] dominance frontier [64..64+NW) per-warp list sizes
   int *hist = ctrl + 128;                                     // 256 bins of the radix select
-  uint32_t *table = reinterpret_cast<uint32_t *>(hist + 256);
+  uint32_t *wqueue = reinterpret_cast<uint32_t *>(hist + 256);  // NW * 64 queued cells awaiting evaluation
+  uint32_t *table = wqueue + NW * 64;
   volatile int *vctrl = ctrl;
 
   const int row_begin = a.bin_bounds[a.bin], row_end = a.bin_bounds[a.bin + 1];
@@ -514,7 +516,7 @@ __global__ void __launch_bounds__(GROUP == 32 ? 256 : GROUP) k_rows(const RowArg
   const int prune_limit = a.cbuf - GROUP;
   const long long N = a.n_users;
   const double xN = xlogx(N);
-  unsigned long long distinct_local = 0;
+  unsigned long long distinct_local = 0, evaluated_local = 0;
   if (gtid < 32) x11tab[gtid] = xlogx((long long)gtid);
 
   for (int ri = row_begin + blockIdx.x * GROUPS + gid; ri < row_end; ri += gridDim.x * GROUPS) {
@@ -604,13 +606,7 @@ __global__ void __launch_bounds__(GROUP == 32 ? 256 : GROUP) k_rows(const RowArg
         n_mine += __popc(m);
         __syncwarp();
       }
-      if (lane == 0) { distinct_local += n_mine; if (NW > 1) ctrl[64 + gw] = (int)n_mine; }
-      int iters = (int)((n_mine + 31) / 32);
-      if (NW > 1) {
-        group_sync<GROUP>();
-        iters = 0;
-        for (int w2 = 0; w2 < NW; ++w2) iters = max(iters, (vctrl[64 + w2] + 31) / 32);
-      }
+      if (lane == 0) distinct_local += n_mine;
       if (a.emit_all) {
         // debug: every non-zero cell of the row (col, count), unordered
         int basepos = 0;
@@ -633,52 +629,73 @@ __global__ void __launch_bounds__(GROUP == 32 ? 256 : GROUP) k_rows(const RowArg
       const double x_ra = x12tab[0], x_nra = x12tab[kX12N];
       const double row_e = varargs ? __dsub_rn(xN, __dadd_rn(__dadd_rn(0.0, x_ra), x_nra))
                                    : __dsub_rn(__dsub_rn(xN, x_ra), x_nra);
-      for (int it = 0; it < iters; ++it) {
-        const uint32_t q = (uint32_t)it * 32 + lane;
-        bool pass_ok = false;
-        uint4 e = make_uint4(0u, 0u, 0u, 0u);
-        if (q < n_mine) {
-          const uint32_t word = table[seg_lo + q];
-          const uint32_t b = word >> cbits, k11 = word & cmask;
-          if (!(a.self && (int)b == item)) {
-            const ColTerm ct = a.col_terms[b];
-            const long long cb = ct.cb;
-            // Dominance filter (exact, DESIGN.md "dominance"): for fixed rowA and N, on the positively associated side
-            // (rowA*cb < k11*N) the LLR grows with k11 and shrinks with cb.  Every evaluated cell (k, c) that fails
-            // strictly on LLR therefore proves that all cells (k' <= k, c' >= c) fail too; cfail[k'] keeps the
-            // smallest such c seen so far for this row, and those cells skip the fp64 evaluation.
-            const bool pos_side = (unsigned long long)ra * (unsigned long long)cb < (unsigned long long)k11 * (unsigned long long)N;
-            const uint32_t kf = k11 < (uint32_t)kDomLevels ? k11 : (uint32_t)kDomLevels;
-            const bool skip = pos_side && k11 <= (uint32_t)kDomLevels && (int)cb >= vctrl[40 + k11];
-            if (!skip) {
-              const long long k21 = cb - k11, k22 = N - ra - cb + k11;
-              const double x11 = k11 < 32 ? x11tab[k11] : xlogx((long long)k11);
-              const double x12 = k11 < kX12N ? x12tab[k11] : xlogx(ra - k11);
-              const double x21 = xlogx(k21), x22 = xlogx(k22);
-              double mat_e;
-              if (varargs)
-                mat_e = __dsub_rn(xN, __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(0.0, x11), x12), x21), x22));
-              else
-                mat_e = __dsub_rn(__dsub_rn(__dsub_rn(__dsub_rn(xN, x11), x12), x21), x22);
-              const double sre = __dadd_rn(row_e, ct.col_e);
-              const double v = (sre < mat_e) ? 0.0 : __dmul_rn(2.0, __dsub_rn(sre, mat_e));
-              const bool min_ok = !a.has_min_llr || v >= a.min_llr;
-              pass_ok = v > 0.0 && min_ok;
-              // (cells whose LLR rounds to 0 are cancellation noise: they teach nothing)
-              bool strict_fail = v > 0.0 && !min_ok;
-              const unsigned long long key = (unsigned long long)__double_as_longlong(v);
-              e = make_uint4((uint32_t)key, (uint32_t)(key >> 32), b, k11);
-              if (pass_ok && vctrl[1]) {
-                const uint4 thr = make_uint4((uint32_t)vctrl[4], (uint32_t)vctrl[5], (uint32_t)vctrl[6], (uint32_t)vctrl[7]);
-                pass_ok = !cand_better(thr, e);
-                strict_fail = e.y < thr.y || (e.y == thr.y && e.x < thr.x);
-              }
-              if (strict_fail && pos_side) {
-                for (uint32_t kk = kf; kk >= 1 && (int)cb < vctrl[40 + kk]; --kk) atomicMin(&ctrl[40 + kk], (int)cb);
-              }
+      // Two stages per warp so that the fp64 evaluation always runs on full warps:
+      //   filter  : 32 cells at a time through the exact dominance filter (integer work only); survivors are queued
+      //   evaluate: 32 queued cells at a time -> LLR -> threshold test -> candidate buffer
+      // One evaluation batch per round, then (CTA-owned rows) one barrier that also decides whether any warp has work.
+      uint32_t *wq = wqueue + gw * 64;
+      uint32_t pos = 0;
+      int qn = 0;
+      while (true) {
+        while (qn < 32 && pos < n_mine) {
+          const uint32_t q = pos + lane;
+          bool surv = false;
+          uint32_t word = 0;
+          if (q < n_mine) {
+            word = table[seg_lo + q];
+            const uint32_t b = word >> cbits, k11 = word & cmask;
+            if (!(a.self && (int)b == item)) {
+              // Dominance filter (exact, DESIGN.md "dominance"): for fixed rowA and N, on the positively associated
+              // side (rowA*cb < k11*N) the LLR grows with k11 and shrinks with cb, so every evaluated cell (k, c) that
+              // fails strictly on LLR proves that all cells (k' <= k, c' >= c) fail too; cfail[k'] = smallest such c.
+              const long long cb = a.marg_b[b];
+              const bool pos_side = (unsigned long long)ra * (unsigned long long)cb < (unsigned long long)k11 * (unsigned long long)N;
+              surv = !(pos_side && k11 <= (uint32_t)kDomLevels && (int)cb >= vctrl[40 + k11]);
             }
           }
+          const unsigned m = __ballot_sync(0xffffffffu, surv);
+          if (surv) wq[qn + __popc(m & ((1u << lane) - 1u))] = word;
+          qn += __popc(m);
+          pos += 32;
+          __syncwarp();
         }
+        const int take = qn < 32 ? qn : 32;
+        bool pass_ok = false;
+        uint4 e = make_uint4(0u, 0u, 0u, 0u);
+        if (lane < take) {
+          const uint32_t word = wq[qn - take + lane];
+          const uint32_t b = word >> cbits, k11 = word & cmask;
+          const ColTerm ct = a.col_terms[b];
+          const long long cb = ct.cb;
+          const bool pos_side = (unsigned long long)ra * (unsigned long long)cb < (unsigned long long)k11 * (unsigned long long)N;
+          const uint32_t kf = k11 < (uint32_t)kDomLevels ? k11 : (uint32_t)kDomLevels;
+          ++evaluated_local;
+          const long long k21 = cb - k11, k22 = N - ra - cb + k11;
+          const double x11 = k11 < 32 ? x11tab[k11] : xlogx((long long)k11);
+          const double x12 = k11 < kX12N ? x12tab[k11] : xlogx(ra - k11);
+          const double x21 = xlogx(k21), x22 = xlogx(k22);
+          double mat_e;
+          if (varargs)
+            mat_e = __dsub_rn(xN, __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(0.0, x11), x12), x21), x22));
+          else
+            mat_e = __dsub_rn(__dsub_rn(__dsub_rn(__dsub_rn(xN, x11), x12), x21), x22);
+          const double sre = __dadd_rn(row_e, ct.col_e);
+          const double v = (sre < mat_e) ? 0.0 : __dmul_rn(2.0, __dsub_rn(sre, mat_e));
+          const bool min_ok = !a.has_min_llr || v >= a.min_llr;
+          pass_ok = v > 0.0 && min_ok;
+          // (cells whose LLR rounds to 0 are cancellation noise: they teach nothing)
+          bool strict_fail = v > 0.0 && !min_ok;
+          const unsigned long long key = (unsigned long long)__double_as_longlong(v);
+          e = make_uint4((uint32_t)key, (uint32_t)(key >> 32), b, k11);
+          if (pass_ok && vctrl[1]) {
+            const uint4 thr = make_uint4((uint32_t)vctrl[4], (uint32_t)vctrl[5], (uint32_t)vctrl[6], (uint32_t)vctrl[7]);
+            pass_ok = !cand_better(thr, e);
+            strict_fail = e.y < thr.y || (e.y == thr.y && e.x < thr.x);
+          }
+          if (strict_fail && pos_side)
+            for (uint32_t kk = kf; kk >= 1 && (int)cb < vctrl[40 + kk]; --kk) atomicMin(&ctrl[40 + kk], (int)cb);
+        }
+        qn -= take;
         const unsigned m = __ballot_sync(0xffffffffu, pass_ok);
         if (m) {
           int basepos = 0;
@@ -686,7 +703,10 @@ __global__ void __launch_bounds__(GROUP == 32 ? 256 : GROUP) k_rows(const RowArg
           basepos = __shfl_sync(0xffffffffu, basepos, 0);
           if (pass_ok) tk[basepos + __popc(m & ((1u << lane) - 1u))] = e;
         }
-        group_sync<GROUP>();
+        const bool more = qn > 0 || pos < n_mine;
+        bool any_more;
+        if (GROUP == 32) { __syncwarp(); any_more = more; }
+        else any_more = __syncthreads_or(more ? 1 : 0) != 0;
         const int n = vctrl[0];
         if (n > prune_limit) {
           if (GROUP > 32 && n <= 512) {
@@ -697,6 +717,7 @@ __global__ void __launch_bounds__(GROUP == 32 ? 256 : GROUP) k_rows(const RowArg
             reduce_candidates<GROUP>(tk, aux, n, a.top_k, a.keep_max, hist, ctrl, gtid);
           }
         }
+        if (!any_more) break;
       }
       group_sync<GROUP>();
     }
@@ -735,6 +756,8 @@ __global__ void __launch_bounds__(GROUP == 32 ? 256 : GROUP) k_rows(const RowArg
   }
   for (int o = 16; o > 0; o >>= 1) distinct_local += __shfl_xor_sync(0xffffffffu, distinct_local, o);
   if (lane == 0 && distinct_local) atomicAdd(a.stat_distinct, distinct_local);
+  for (int o = 16; o > 0; o >>= 1) evaluated_local += __shfl_xor_sync(0xffffffffu, evaluated_local, o);
+  if (lane == 0 && evaluated_local) atomicAdd(a.stat_evaluated, evaluated_local);
 }
 
 // packed output: gather the strided per-row results into CSR order

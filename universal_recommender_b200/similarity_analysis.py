@@ -34,6 +34,7 @@ class TrainStats:
     products: list
     distinct_cells: list
     out_nnz: list
+    llr_evaluated: list
     ms_h2d: float
     ms_prepare: float
     ms_cooccurrence: float
@@ -140,7 +141,7 @@ class CcoContext:
             st = N.StatsT()
             N.check(L.cco_result_stats(res, C.byref(st)))
             self.last_stats = TrainStats(st.n_users, st.nnz_in_total, list(st.nnz_downsampled)[:n], list(st.products)[:n],
-                                         list(st.distinct_cells)[:n], list(st.out_nnz)[:n], st.ms_h2d, st.ms_prepare,
+                                         list(st.distinct_cells)[:n], list(st.out_nnz)[:n], list(st.llr_evaluated)[:n], st.ms_h2d, st.ms_prepare,
                                          st.ms_cooccurrence, st.ms_total, list(st.ms_indicator)[:n], st.n_kernel_launches)
             return out
         finally:
