@@ -308,7 +308,7 @@ static int next_pow2(int x) {
 
 template <int GROUP>
 static int launch_rows_t(cco_ctx *c, const RowArgs &a, BinCfg &cfg, cudaStream_t st) {
-  constexpr int CTA = GROUP == 32 ? 256 : GROUP;
+  constexpr int CTA = GROUP == 32 ? 64 : GROUP;   // warp-owned rows: two independent warps per CTA (fine-grained smem packing)
   int occ = 1;
   void (*kern)(const RowArgs) = cfg.dense ? k_rows<GROUP, true> : k_rows<GROUP, false>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
@@ -332,7 +332,7 @@ static int launch_rows(cco_ctx *c, const RowArgs &a, BinCfg &cfg, cudaStream_t s
 
 static BinCfg make_cfg(cco_ctx *c, int group, int want_slots, int top_k, int n_cols_b) {
   BinCfg f;
-  const int groups = group == 32 ? 8 : 1;
+  const int groups = group == 32 ? 2 : 1;
   f.group = group;
   f.final_max = next_pow2(top_k);
   f.cbuf = next_pow2(top_k + std::max(group, 128) + (group == 32 ? 64 : 0));
@@ -420,11 +420,24 @@ static int run_indicator(cco_ctx *c, Arena &ar, const uint32_t *at_ptr, const in
   // 2. bins -----------------------------------------------------------------------------------------
   const int k_eff = emit_all ? 1 : prm.top_k;
   const bool warp_ok = k_eff + 32 <= 256;  // warp-owned rows keep a 256-entry candidate buffer
-  BinCfg cfgL = make_cfg(c, 1024, 1 << 20, k_eff, n_cols_b);
-  BinCfg cfgD = make_cfg(c, 512, 16384, k_eff, n_cols_b);
-  BinCfg cfgC = make_cfg(c, 256, 8192, k_eff, n_cols_b);
-  BinCfg cfgG = make_cfg(c, 128, 4096, k_eff, n_cols_b);
-  BinCfg cfgW = make_cfg(c, 32, 512, k_eff, n_cols_b);
+  // Work bins, largest rows first.  {threads that own a row, table words, largest row work w the bin takes}.
+  // Bin 0 is the multi-pass bin (same config as bin 1).  Rows up to 2048 products are WARP-owned: no CTA barrier
+  // anywhere in their count / compact / score / select pipeline (profiles/r01_k_rows_ncu_full.md: barriers cost the
+  // CTA-owned bins 35-45 % of their warp time); larger rows need the table and the parallelism of a whole CTA.
+  struct BinSpec { int group, slots; uint32_t max_w; };
+  std::vector<BinSpec> spec = {{1024, 1 << 20, 0xffffffffu}, {1024, 1 << 20, 0xffffffffu}, {512, 16384, 8192u}, {256, 8192, 4096u}};
+  if (warp_ok) {
+    spec.push_back({32, 4096, 2048u});
+    spec.push_back({32, 2048, 1024u});
+    spec.push_back({32, 1024, 512u});
+    spec.push_back({32, 512, 256u});
+  } else {
+    spec.push_back({128, 4096, 2048u});
+  }
+  const int kBins = (int)spec.size();
+  std::vector<BinCfg> cfgs(kBins);
+  for (int b = 0; b < kBins; ++b) cfgs[b] = make_cfg(c, spec[b].group, spec[b].slots, k_eff, n_cols_b);
+  BinCfg &cfgL = cfgs[1];
   // packed word: key bits must leave room for the largest possible count (= users of the item)
   int key_bits = 1;
   while (((1LL << key_bits) - 1) <= (long long)n_cols_b) ++key_bits;  // keys <= 2^kb - 2
@@ -433,18 +446,21 @@ static int run_indicator(cco_ctx *c, Arena &ar, const uint32_t *at_ptr, const in
     return set_error(CCO_E_UNSUPPORTED,
                      "an item with %d users and %d columns does not fit the packed 32-bit accumulator word "
                      "(key %d bits + count %d bits)", max_marg_a, n_cols_b, key_bits, count_bits);
-  // bins by WORK w (descending thresholds): 0 = multi-pass L, 1 = L (1024 threads/row), 2 = D (512), 3 = C (256),
-  // 4 = G (128), 5 = W (one warp/row); rows with w == 0 produce nothing.
-  auto thr = [&](const BinCfg &f) -> uint32_t { return f.dense ? 0xffffffffu : (uint32_t)f.cap; };
-  constexpr int kBins = 6;
-  uint32_t h_thr[kBins] = {thr(cfgL), std::min<uint32_t>(thr(cfgD), 8192u), std::min<uint32_t>(thr(cfgC), 4096u),
-                           std::min<uint32_t>(thr(cfgG), 2048u), warp_ok ? std::min<uint32_t>(thr(cfgW), 256u) : 0u, 0u};
-  for (int b = 1; b < kBins; ++b) h_thr[b] = std::min(h_thr[b], h_thr[b - 1]);
+  // thresholds on w, descending: bin b takes rows with h_thr[b-1] >= w > h_thr[b]; a hashed table also needs w <= cap
+  std::vector<uint32_t> h_thr(kBins);
+  for (int b = 0; b < kBins; ++b) {
+    const BinCfg &f = cfgs[std::min(b + 1, kBins - 1)];   // h_thr[b] = upper limit of bin b+1
+    uint32_t lim = b + 1 < kBins ? spec[b + 1].max_w : 0u;
+    if (b + 1 < kBins && !f.dense) lim = std::min<uint32_t>(lim, (uint32_t)f.cap);
+    h_thr[b] = lim;
+    if (b > 0) h_thr[b] = std::min(h_thr[b], h_thr[b - 1]);
+  }
   uint32_t *d_thr;
   int32_t *d_bounds;
   CKR(ar.alloc(&d_thr, kBins));
   CKR(ar.alloc(&d_bounds, kBins + 3));
-  CK(cudaMemcpyAsync(d_thr, h_thr, sizeof h_thr, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(d_thr, h_thr.data(), sizeof(uint32_t) * kBins, cudaMemcpyHostToDevice, s));
+  CK(cudaStreamSynchronize(s));  // h_thr is a local vector
   k_bin_bounds<<<1, 32, 0, s>>>(n_my, sorted_work, kBins, d_thr, d_bounds);
   c->launches++;
   // per-column constants of B' for the fused LLR
@@ -502,23 +518,21 @@ static int run_indicator(cco_ctx *c, Arena &ar, const uint32_t *at_ptr, const in
   a.emit_all = emit_all ? 1 : 0;
   CK(cudaEventRecord(c->ev[4], s));
   if (n_my > 0) {
-    BinCfg *cfgs[kBins] = {&cfgL, &cfgL, &cfgD, &cfgC, &cfgG, &cfgW};
     // the bins touch disjoint rows: run them concurrently (tails of one bin overlap the bulk of another)
     CK(cudaEventRecord(c->bin_ev[8], s));
     for (int b = 0; b < kBins; ++b) {
       if (b == 0 && cfgL.dense) continue;                 // dense L takes every large row in bin 1
-      if (b == 5 && !warp_ok) continue;                   // large top_k: the 128-thread kernel takes the smallest rows too
       RowArgs ab = a;
       ab.bin = b;
-      ab.slots = cfgs[b]->slots;
-      ab.cap = cfgs[b]->cap;
-      ab.cbuf = cfgs[b]->cbuf;
-      ab.caux = cfgs[b]->caux;
-      ab.keep_max = cfgs[b]->keep_max;
-      ab.final_max = cfgs[b]->final_max;
-      ab.group_smem_bytes = (int32_t)cfgs[b]->region;
+      ab.slots = cfgs[b].slots;
+      ab.cap = cfgs[b].cap;
+      ab.cbuf = cfgs[b].cbuf;
+      ab.caux = cfgs[b].caux;
+      ab.keep_max = cfgs[b].keep_max;
+      ab.final_max = cfgs[b].final_max;
+      ab.group_smem_bytes = (int32_t)cfgs[b].region;
       CK(cudaStreamWaitEvent(c->bin_stream[b], c->bin_ev[8], 0));
-      CKR(launch_rows(c, ab, *cfgs[b], c->bin_stream[b]));
+      CKR(launch_rows(c, ab, cfgs[b], c->bin_stream[b]));
       CK(cudaEventRecord(c->bin_ev[b], c->bin_stream[b]));
       CK(cudaStreamWaitEvent(s, c->bin_ev[b], 0));
     }

@@ -492,8 +492,7 @@ __device__ __forceinline__ void accumulate(uint32_t *table, uint32_t tsize, uint
 
 template <int GROUP, bool DENSE>
 __global__ void __launch_bounds__(GROUP == 32 ? 256 : GROUP) k_rows(const RowArgs a) {
-  constexpr int CTA = GROUP == 32 ? 256 : GROUP;
-  constexpr int GROUPS = CTA / GROUP;
+  const int GROUPS = GROUP == 32 ? (int)(blockDim.x >> 5) : 1;  // warp-owned rows: several independent warps per CTA
   constexpr int NW = GROUP / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31;
