@@ -41,7 +41,7 @@ UNIT = "events/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("CCO_BENCH_WORKLOAD", "C3"))
@@ -61,7 +61,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
                                        "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -320,7 +320,9 @@ def main():
                        "resident": "value: matrices resident in HBM, indicators left packed in HBM",
                        "products_per_step": int(sum_over_ranks(float(sum(st_last.products)))),
                        "distinct_cells_per_step": int(sum_over_ranks(float(sum(st_last.distinct_cells)))),
-                       "datagen_s": round(t_gen, 1)},
+                       "datagen_s": round(t_gen, 1),
+                       "stage_ms_last_resident_step": {"prepare": round(st_last.ms_prepare, 3), "indicators_total": round(st_last.ms_cooccurrence, 3),
+                                                       "row_kernels": [round(x, 3) for x in st_last.ms_indicator]}},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
                     "ms_per_step": ms_e2e},

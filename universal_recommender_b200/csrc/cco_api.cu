@@ -99,6 +99,7 @@ struct cco_ctx {
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev[8] = {};
   cudaEvent_t tev[2] = {};
+  cudaEvent_t copy_ev[2] = {};
   cudaStream_t bin_stream[8] = {};
   cudaEvent_t bin_ev[9] = {};
   std::vector<PinnedBuf> pinned;
@@ -577,18 +578,23 @@ static int run_indicator(cco_ctx *c, Arena &ar, const uint32_t *at_ptr, const in
   rm->cnt = (int32_t *)c->pinned_get(sizeof(int32_t) * (size_t)std::max<long long>(total, 1));
   rm->llr = (double *)c->pinned_get(sizeof(double) * (size_t)std::max<long long>(total, 1));
   if (!rm->row_ptr || !rm->col || !rm->cnt || !rm->llr) return set_error(CCO_E_OOM, "pinned host allocation failed");
-  CK(cudaMemcpyAsync(rm->row_ptr, out_ptr, sizeof(int64_t) * ((size_t)n_my + 1), cudaMemcpyDeviceToHost, s));
+  // device -> host on the copy stream so the transfer overlaps the next indicator's kernels; train_dataset joins the
+  // copy stream before it returns (and before the arena frees the packed buffers)
+  cudaStream_t cs = c->copy_stream;
+  CK(cudaEventRecord(c->copy_ev[0], s));
+  CK(cudaStreamWaitEvent(cs, c->copy_ev[0], 0));
+  CK(cudaMemcpyAsync(rm->row_ptr, out_ptr, sizeof(int64_t) * ((size_t)n_my + 1), cudaMemcpyDeviceToHost, cs));
   if (total > 0 && !(flags & CCO_FLAG_RESULT_ON_DEVICE)) {
-    CK(cudaMemcpyAsync(rm->col, p_col, sizeof(int32_t) * (size_t)total, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(rm->cnt, p_cnt, sizeof(int32_t) * (size_t)total, cudaMemcpyDeviceToHost, s));
-    if (!emit_all) CK(cudaMemcpyAsync(rm->llr, p_llr, sizeof(double) * (size_t)total, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(rm->col, p_col, sizeof(int32_t) * (size_t)total, cudaMemcpyDeviceToHost, cs));
+    CK(cudaMemcpyAsync(rm->cnt, p_cnt, sizeof(int32_t) * (size_t)total, cudaMemcpyDeviceToHost, cs));
+    if (!emit_all) CK(cudaMemcpyAsync(rm->llr, p_llr, sizeof(double) * (size_t)total, cudaMemcpyDeviceToHost, cs));
   }
-  CK(cudaStreamSynchronize(s));
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]));
   if (ms_rows) *ms_rows = ms;
-  // release the big per-indicator buffers early
-  for (void *p : {(void *)o_col, (void *)o_cnt, (void *)o_llr, (void *)p_col, (void *)p_cnt, (void *)p_llr})
+  // the strided buffers are dead once k_compact_rows has been enqueued (stream order); the packed ones stay until the
+  // copy stream is joined
+  for (void *p : {(void *)o_col, (void *)o_cnt, (void *)o_llr})
     if (p) ar.release(p);
   return CCO_OK;
 }
@@ -705,6 +711,10 @@ static int train_dataset(cco_ctx *c, const cco_dataset *ds, const cco_indicator_
   cudaStream_t s = c->stream;
   const int n_mats = ds->n_mats;
   Arena ar(s);
+  struct CopyJoin {  // destroyed before `ar`: no packed buffer is freed while the copy stream still reads it
+    cco_ctx *c;
+    ~CopyJoin() { cudaStreamSynchronize(c->copy_stream); }
+  } copy_join{c};
   cco_result *res = new cco_result();
   res->ctx = c;
   res->mats.resize(n_mats);
@@ -804,8 +814,11 @@ static int train_dataset(cco_ctx *c, const cco_dataset *ds, const cco_indicator_
       st.ms_indicator[i] = ms_rows;
     }
   }
+  CK(cudaEventRecord(c->copy_ev[1], c->copy_stream));
+  CK(cudaStreamWaitEvent(s, c->copy_ev[1], 0));
   CK(cudaEventRecord(c->ev[3], s));
   CK(cudaStreamSynchronize(s));
+  CK(cudaStreamSynchronize(c->copy_stream));
   CK(cudaEventElapsedTime(&st.ms_prepare, c->ev[1], c->ev[2]));
   CK(cudaEventElapsedTime(&st.ms_cooccurrence, c->ev[2], c->ev[3]));
   CK(cudaEventElapsedTime(&st.ms_total, c->ev[1], c->ev[3]));
@@ -896,6 +909,7 @@ int cco_create(const cco_config_t *cfg, cco_ctx_t **out) {
   CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   for (auto &ev : c->ev) CK(cudaEventCreate(&ev));
   for (auto &ev : c->tev) CK(cudaEventCreate(&ev));
+  for (auto &ev : c->copy_ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   for (auto &st : c->bin_stream) CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   for (auto &ev : c->bin_ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   cudaMemPool_t pool;
@@ -933,6 +947,8 @@ int cco_destroy(cco_ctx_t *c) {
   for (auto &ev : c->ev)
     if (ev) cudaEventDestroy(ev);
   for (auto &ev : c->tev)
+    if (ev) cudaEventDestroy(ev);
+  for (auto &ev : c->copy_ev)
     if (ev) cudaEventDestroy(ev);
   for (auto &st : c->bin_stream)
     if (st) cudaStreamDestroy(st);
@@ -1192,6 +1208,7 @@ int cco_debug_cooccurrence(cco_ctx_t *c, const cco_csr_t *a, const cco_csr_t *b,
   cco_indicator_params_t p1 = {0x7fffffff, 1, 0, 0.0};
   int rc = run_indicator(c, ar, at_ptr, at_users, n_items_a, dm[0].marg, max_marg_a, dm[1], a->n_rows, false, p1, 0, true, 0, 1,
                          &rm, &io, nullptr);
+  cudaStreamSynchronize(c->copy_stream);
   auto put = [&]() {
     for (void *p : {(void *)rm.row_ptr, (void *)rm.col, (void *)rm.llr, (void *)rm.cnt})
       if (p) c->pinned_put(p);

@@ -173,14 +173,20 @@ __global__ void k_col_histogram(long long row_begin, long long row_end, const lo
   }
 }
 
-__device__ __forceinline__ double sample_rate(long long d, double c, int32_t m, bool intdiv) {
-  double row_rate = 1.0;
-  if (d > 0) {
-    long long md = d < m ? d : (long long)m;
-    row_rate = intdiv ? (double)(md / d) : __ddiv_rn((double)md, (double)d);
-  }
-  double col_rate = __ddiv_rn(c < (double)m ? c : (double)m, c);
-  return row_rate < col_rate ? row_rate : col_rate;
+// perRowSampleRate of sampleDownAndBinarize (hoisted: once per row)
+__device__ __forceinline__ double row_sample_rate(long long d, int32_t m, bool intdiv) {
+  if (d <= 0) return 1.0;
+  const long long md = d < m ? d : (long long)m;
+  return intdiv ? (double)(md / d) : __ddiv_rn((double)md, (double)d);
+}
+// keep (row, j)?  Bit-identical to oracle/cco_oracle.c orc_downsample: the sample rate is exactly 1.0 whenever the
+// row and the column are within m (x/x == 1.0 in IEEE), and u01 < 1, so those entries skip the hash and the division.
+__device__ __forceinline__ bool keep_entry(long long d, double row_rate, int32_t c, int32_t m, int32_t seed, uint32_t row,
+                                           uint32_t j) {
+  if (d <= m && c <= m) return true;
+  const double col_rate = c <= m ? 1.0 : __ddiv_rn((double)m, (double)c);
+  const double rate = row_rate < col_rate ? row_rate : col_rate;
+  return sample_u01(seed, row, j) <= rate;
 }
 
 // pass 1 of sampleDownAndBinarize: kept entries per row + post-sample column marginals
@@ -195,6 +201,7 @@ __global__ void k_downsample_count(long long n_rows, const long long *__restrict
   // all lanes of a sub-group share `row`, so loop trip counts are sub-group uniform
   for (; row < n_rows; row += stride) {
     long long s = rp[row], e = rp[row + 1], d = e - s;
+    const double row_rate = row_sample_rate(d, m, intdiv);
     uint32_t kept = 0;
     for (long long q0 = s; q0 < e; q0 += kSG) {
       long long q = q0 + lane;
@@ -202,8 +209,7 @@ __global__ void k_downsample_count(long long n_rows, const long long *__restrict
       int32_t j = 0;
       if (q < e) {
         j = col[q];
-        double rate = sample_rate(d, (double)raw_counts[j], m, intdiv);
-        keep = sample_u01(seed, (uint32_t)row, (uint32_t)j) <= rate;
+        keep = keep_entry(d, row_rate, raw_counts[j], m, seed, (uint32_t)row, (uint32_t)j);
       }
       if (keep) atomicAdd(&new_counts[j], 1);
       kept += __popc(__ballot_sync(sg_mask, keep) & sg_mask);
@@ -224,6 +230,7 @@ __global__ void k_downsample_write(long long n_rows, const long long *__restrict
   const bool intdiv = (flags & CCO_FLAG_ROWRATE_INTDIV) != 0;
   for (; row < n_rows; row += stride) {
     long long s = rp[row], e = rp[row + 1], d = e - s;
+    const double row_rate = row_sample_rate(d, m, intdiv);
     uint32_t w = new_ptr[row];
     for (long long q0 = s; q0 < e; q0 += kSG) {
       long long q = q0 + lane;
@@ -231,8 +238,7 @@ __global__ void k_downsample_write(long long n_rows, const long long *__restrict
       int32_t j = 0;
       if (q < e) {
         j = col[q];
-        double rate = sample_rate(d, (double)raw_counts[j], m, intdiv);
-        keep = sample_u01(seed, (uint32_t)row, (uint32_t)j) <= rate;
+        keep = keep_entry(d, row_rate, raw_counts[j], m, seed, (uint32_t)row, (uint32_t)j);
       }
       unsigned b = (__ballot_sync(sg_mask, keep) & sg_mask) >> sg_shift;
       if (keep) new_col[w + __popc(b & ((1u << lane) - 1u))] = j;
