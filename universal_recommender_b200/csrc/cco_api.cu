@@ -106,6 +106,11 @@ struct cco_ctx {
   std::mutex mu;
   ncclComm_t comm = nullptr;
   int launches = 0;
+  // mailbox for small device -> host results (mapped pinned memory written by k_mail_bytes)
+  unsigned char *mail_h = nullptr, *mail_d = nullptr;
+  size_t mail_used = 0;
+  struct MailItem { void *dst; size_t off, n; };
+  std::vector<MailItem> mail_pending;
 
   void *pinned_get(size_t bytes) {
     std::lock_guard<std::mutex> lk(mu);
@@ -145,6 +150,8 @@ struct cco_dataset {
   std::vector<long long> n_cols, nnz;
   std::vector<long long *> rp;   // device, int64 [n_users+1]
   std::vector<int32_t *> col;    // device
+  std::vector<cudaEvent_t> ready;  // per matrix: host->device copy finished (copy stream)
+  bool h2d_pending = false;        // uploaded asynchronously: ms_h2d is read when the train joins
   float ms_h2d = 0;
 };
 
@@ -190,6 +197,25 @@ static inline int grid_for(long long work_items, int block, int sm_count, int wa
   if (g > cap) g = cap;
   if (g < 1) g = 1;
   return (int)g;
+}
+
+constexpr size_t kMailBytes = 1 << 16;
+// enqueue "copy n bytes from device to *dst_host"; the value is there after mail_wait()
+static int mail_fetch(cco_ctx *c, void *dst_host, const void *src_dev, size_t n) {
+  size_t off = (c->mail_used + 7) & ~(size_t)7;
+  if (off + n > kMailBytes) return set_error(CCO_E_CUDA, "internal: mailbox overflow");
+  k_mail_bytes<<<1, 128, 0, c->stream>>>(c->mail_d + off, (const unsigned char *)src_dev, (int)n);
+  c->mail_pending.push_back({dst_host, off, n});
+  c->mail_used = off + n;
+  return CCO_OK;
+}
+static int mail_wait(cco_ctx *c) {
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaGetLastError());
+  for (auto &m : c->mail_pending) memcpy(m.dst, c->mail_h + m.off, m.n);
+  c->mail_pending.clear();
+  c->mail_used = 0;
+  return CCO_OK;
 }
 
 struct DevRaw {  // a matrix as uploaded (int64 row_ptr like the host)
@@ -380,32 +406,23 @@ static int run_indicator(cco_ctx *c, Arena &ar, const uint32_t *at_ptr, const in
   CKR(exclusive_sum_i64(c, ar, (const long long *)work64, work_prefix, (long long)n_items_a + 1));
   // rank partition: contiguous item ranges balanced by work prefix (identical on every rank)
   int32_t row_lo = 0, row_hi = n_items_a;
-  long long total_work = 0;
-  {
-    std::vector<long long> hp;
-    CK(cudaMemcpyAsync(&total_work, work_prefix + n_items_a, 8, cudaMemcpyDeviceToHost, s));
-    if (world > 1) {
-      hp.resize((size_t)n_items_a + 1);
-      CK(cudaMemcpyAsync(hp.data(), work_prefix, sizeof(long long) * ((size_t)n_items_a + 1), cudaMemcpyDeviceToHost, s));
-    }
-    CK(cudaStreamSynchronize(s));
-    if (world > 1) {
-      std::vector<int32_t> bounds((size_t)world + 1);
-      CKR(cco_partition_rows(reinterpret_cast<const int64_t *>(hp.data()), n_items_a, world, bounds.data()));
-      row_lo = bounds[rank];
-      row_hi = bounds[rank + 1];
-    }
+  if (world > 1) {
+    int32_t *d_pb;
+    std::vector<int32_t> bounds((size_t)world + 1);
+    CKR(ar.alloc(&d_pb, world + 1));
+    k_partition_rows<<<1, 64, 0, s>>>(work_prefix, n_items_a, world, d_pb);   // world <= 63 ranks per job
+    c->launches++;
+    CKR(mail_fetch(c, bounds.data(), d_pb, sizeof(int32_t) * ((size_t)world + 1)));
+    CKR(mail_wait(c));
+    row_lo = bounds[rank];
+    row_hi = bounds[rank + 1];
   }
   const int32_t n_my = row_hi - row_lo;
   io->row_begin = row_lo;
   io->row_end = row_hi;
-  {
-    long long hp2[2] = {0, 0};
-    CK(cudaMemcpyAsync(&hp2[0], work_prefix + row_lo, 8, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(&hp2[1], work_prefix + row_hi, 8, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    io->products = hp2[1] - hp2[0];
-  }
+  long long hp2[2] = {0, 0};   // filled by the mailbox before the final sync of this indicator
+  CKR(mail_fetch(c, &hp2[0], work_prefix + row_lo, 8));
+  CKR(mail_fetch(c, &hp2[1], work_prefix + row_hi, 8));
   CKR(ar.alloc(&sorted_work, n_my + 1));
   CKR(ar.alloc(&rows_sorted, n_my + 1));
   if (n_my > 0) {
@@ -552,10 +569,11 @@ static int run_indicator(cco_ctx *c, Arena &ar, const uint32_t *at_ptr, const in
   long long total = 0;
   unsigned long long h_distinct[2] = {0, 0};
   int h_err = 0;
-  CK(cudaMemcpyAsync(&total, out_ptr + n_my, 8, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(h_distinct, d_distinct, 16, cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(&h_err, d_err, 4, cudaMemcpyDeviceToHost, s));
-  CK(cudaStreamSynchronize(s));
+  CKR(mail_fetch(c, &total, out_ptr + n_my, 8));
+  CKR(mail_fetch(c, h_distinct, d_distinct, 16));
+  CKR(mail_fetch(c, &h_err, d_err, 4));
+  CKR(mail_wait(c));
+  io->products = hp2[1] - hp2[0];
   if (h_err) return set_error(CCO_E_CUDA, "internal: shared-memory hash table overflow");
   io->nnz = total;
   io->distinct = (int64_t)h_distinct[0];
@@ -631,10 +649,12 @@ static void dataset_release(cco_dataset *d) {
     if (p) cudaFreeAsync(p, d->ctx->stream);
   for (auto p : d->col)
     if (p) cudaFreeAsync(p, d->ctx->stream);
+  for (auto e : d->ready)
+    if (e) cudaEventDestroy(e);
   delete d;
 }
 
-static int dataset_upload(cco_ctx *c, int32_t n_mats, const cco_csr_t *mats, uint32_t flags, cco_dataset **out) {
+static int dataset_upload(cco_ctx *c, int32_t n_mats, const cco_csr_t *mats, uint32_t flags, cco_dataset **out, bool async = false) {
   CK(cudaSetDevice(c->device));
   cudaStream_t s = c->stream;
   cco_dataset *d = new cco_dataset();
@@ -645,6 +665,7 @@ static int dataset_upload(cco_ctx *c, int32_t n_mats, const cco_csr_t *mats, uin
   d->col.assign(n_mats, nullptr);
   d->n_cols.assign(n_mats, 0);
   d->nnz.assign(n_mats, 0);
+  d->ready.assign(n_mats, nullptr);
   struct G {
     cco_dataset *d;
     bool ok = false;
@@ -652,7 +673,9 @@ static int dataset_upload(cco_ctx *c, int32_t n_mats, const cco_csr_t *mats, uin
       if (!ok) dataset_release(d);
     }
   } g{d};
-  CK(cudaEventRecord(c->ev[6], s));
+  // allocations are ordered on the main stream; the copies run on the copy stream (H2D engine) so that the caller
+  // of the async form can start preparing matrix i while matrix i+1 is still in flight
+  cudaStream_t cs = c->copy_stream;
   for (int i = 0; i < n_mats; ++i) {
     const cco_csr_t &m = mats[i];
     d->n_cols[i] = m.n_cols;
@@ -664,11 +687,26 @@ static int dataset_upload(cco_ctx *c, int32_t n_mats, const cco_csr_t *mats, uin
     e = cudaMallocAsync(&p, sizeof(int32_t) * (size_t)std::max<long long>(d->nnz[i], 4), s);
     if (e != cudaSuccess) return set_error(CCO_E_OOM, "cudaMallocAsync col_idx: %s", cudaGetErrorString(e));
     d->col[i] = (int32_t *)p;
-    CK(cudaMemcpyAsync(d->rp[i], m.row_ptr, sizeof(int64_t) * ((size_t)m.n_rows + 1), cudaMemcpyHostToDevice, s));
-    if (d->nnz[i] > 0)
-      CK(cudaMemcpyAsync(d->col[i], m.col_idx, sizeof(int32_t) * (size_t)d->nnz[i], cudaMemcpyHostToDevice, s));
+    CK(cudaEventCreateWithFlags(&d->ready[i], cudaEventDisableTiming));
   }
-  CK(cudaEventRecord(c->ev[7], s));
+  CK(cudaEventRecord(c->copy_ev[0], s));
+  CK(cudaStreamWaitEvent(cs, c->copy_ev[0], 0));
+  CK(cudaEventRecord(c->ev[6], cs));
+  for (int i = 0; i < n_mats; ++i) {
+    const cco_csr_t &m = mats[i];
+    CK(cudaMemcpyAsync(d->rp[i], m.row_ptr, sizeof(int64_t) * ((size_t)m.n_rows + 1), cudaMemcpyHostToDevice, cs));
+    if (d->nnz[i] > 0)
+      CK(cudaMemcpyAsync(d->col[i], m.col_idx, sizeof(int32_t) * (size_t)d->nnz[i], cudaMemcpyHostToDevice, cs));
+    CK(cudaEventRecord(d->ready[i], cs));
+  }
+  CK(cudaEventRecord(c->ev[7], cs));
+  if (async && (flags & CCO_FLAG_ASSUME_CANONICAL)) {
+    d->h2d_pending = true;
+    g.ok = true;
+    *out = d;
+    return CCO_OK;
+  }
+  for (int i = 0; i < n_mats; ++i) CK(cudaStreamWaitEvent(s, d->ready[i], 0));
   // check + (if needed) canonicalise in place
   if (!(flags & CCO_FLAG_ASSUME_CANONICAL)) {
     Arena ar(s);
@@ -710,6 +748,8 @@ static int train_dataset(cco_ctx *c, const cco_dataset *ds, const cco_indicator_
   CK(cudaSetDevice(c->device));
   cudaStream_t s = c->stream;
   const int n_mats = ds->n_mats;
+  c->mail_pending.clear();
+  c->mail_used = 0;
   Arena ar(s);
   struct CopyJoin {  // destroyed before `ar`: no packed buffer is freed while the copy stream still reads it
     cco_ctx *c;
@@ -730,6 +770,7 @@ static int train_dataset(cco_ctx *c, const cco_dataset *ds, const cco_indicator_
   st.n_mats = n_mats;
   st.n_users = ds->n_users;
   st.ms_h2d = ds->ms_h2d;
+  const bool h2d_pending = ds->h2d_pending;
   const long long n_users = ds->n_users;
   std::vector<DevRaw> raw(n_mats);
   for (int i = 0; i < n_mats; ++i) {
@@ -754,6 +795,7 @@ static int train_dataset(cco_ctx *c, const cco_dataset *ds, const cco_indicator_
   CK(cudaMemsetAsync(raw_counts, 0, sizeof(int32_t) * (size_t)std::max<long long>(total_cols, 1), s));
   const long long u_lo = n_users * c->rank / c->world, u_hi = n_users * (c->rank + 1) / c->world;
   for (int i = 0; i < n_mats; ++i) {
+    CK(cudaStreamWaitEvent(s, ds->ready[i], 0));  // matrix i has landed (async upload: later ones may still be in flight)
     if (raw[i].nnz == 0 || u_hi == u_lo) continue;
     k_col_histogram<<<grid_for(raw[i].nnz / c->world + 1, 256, c->sm_count), 256, 0, s>>>(u_lo, u_hi, raw[i].rp, raw[i].col,
                                                                                        raw_counts + col_off[i]);
@@ -793,12 +835,10 @@ static int train_dataset(cco_ctx *c, const cco_dataset *ds, const cco_indicator_
   }
   int32_t max_marg_a = 0;
   std::vector<uint32_t> h_nnz(n_mats);
-  CK(cudaMemcpyAsync(&max_marg_a, d_max, 4, cudaMemcpyDeviceToHost, s));
-  for (int i = 0; i < n_mats; ++i)
-    CK(cudaMemcpyAsync(&h_nnz[i], dm[i].rp + n_users, 4, cudaMemcpyDeviceToHost, s));
+  CKR(mail_fetch(c, &max_marg_a, d_max, 4));
+  for (int i = 0; i < n_mats; ++i) CKR(mail_fetch(c, &h_nnz[i], dm[i].rp + n_users, 4));
   CK(cudaEventRecord(c->ev[2], s));
-  CK(cudaStreamSynchronize(s));
-  CK(cudaGetLastError());
+  CKR(mail_wait(c));
   for (int i = 0; i < n_mats && i < 16; ++i) st.nnz_downsampled[i] = h_nnz[i];
 
   for (int i = 0; i < n_mats; ++i) {
@@ -819,10 +859,11 @@ static int train_dataset(cco_ctx *c, const cco_dataset *ds, const cco_indicator_
   CK(cudaEventRecord(c->ev[3], s));
   CK(cudaStreamSynchronize(s));
   CK(cudaStreamSynchronize(c->copy_stream));
+  if (h2d_pending) CK(cudaEventElapsedTime(&st.ms_h2d, c->ev[6], c->ev[7]));
   CK(cudaEventElapsedTime(&st.ms_prepare, c->ev[1], c->ev[2]));
   CK(cudaEventElapsedTime(&st.ms_cooccurrence, c->ev[2], c->ev[3]));
   CK(cudaEventElapsedTime(&st.ms_total, c->ev[1], c->ev[3]));
-  st.ms_total += st.ms_h2d;
+  if (!h2d_pending) st.ms_total += st.ms_h2d;  // async upload overlaps the prepare stage: already inside the bracket
   st.n_kernel_launches = c->launches;
   guard.ok = true;
   *out = res;
@@ -834,8 +875,9 @@ static int train_impl(cco_ctx *c, int32_t n_mats, const cco_csr_t *mats, const c
   CKR(validate_host(n_mats, mats, params));
   c->launches = 0;
   cco_dataset *ds = nullptr;
-  CKR(dataset_upload(c, n_mats, mats, flags, &ds));
+  CKR(dataset_upload(c, n_mats, mats, flags, &ds, /*async=*/true));
   int rc = train_dataset(c, ds, params, seed, flags, out);
+  cudaStreamSynchronize(c->copy_stream);  // the caller's host buffers are free again when cco_train returns
   dataset_release(ds);
   return rc;
 }
@@ -912,6 +954,8 @@ int cco_create(const cco_config_t *cfg, cco_ctx_t **out) {
   for (auto &ev : c->copy_ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   for (auto &st : c->bin_stream) CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   for (auto &ev : c->bin_ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  CK(cudaHostAlloc((void **)&c->mail_h, kMailBytes, cudaHostAllocMapped));
+  CK(cudaHostGetDevicePointer((void **)&c->mail_d, c->mail_h, 0));
   cudaMemPool_t pool;
   CK(cudaDeviceGetDefaultMemPool(&pool, cfg->device));
   uint64_t thr = UINT64_MAX;
@@ -944,6 +988,7 @@ int cco_destroy(cco_ctx_t *c) {
   cudaStreamSynchronize(c->stream);
   if (c->comm) g_nccl.CommDestroy(c->comm);
   for (auto &b : c->pinned) cudaFreeHost(b.p);
+  if (c->mail_h) cudaFreeHost(c->mail_h);
   for (auto &ev : c->ev)
     if (ev) cudaEventDestroy(ev);
   for (auto &ev : c->tev)
@@ -1164,6 +1209,8 @@ int cco_debug_cooccurrence(cco_ctx_t *c, const cco_csr_t *a, const cco_csr_t *b,
   cco_indicator_params_t prm[2] = {{0x7fffffff, 1, 0, 0.0}, {0x7fffffff, 1, 0, 0.0}};
   CKR(validate_host(2, two, prm));
   CK(cudaSetDevice(c->device));
+  c->mail_pending.clear();
+  c->mail_used = 0;
   cudaStream_t s = c->stream;
   cco_dataset *ds = nullptr;
   CKR(dataset_upload(c, 2, two, 0, &ds));

@@ -821,6 +821,30 @@ __global__ void k_rowptr_from_keys(long long n_rows, long long n_unique, const u
   }
 }
 
+// small device -> host results go through a mapped pinned "mailbox" written by this kernel, not through the D2H copy
+// engine: a few-byte cudaMemcpyAsync would queue behind the multi-megabyte indicator copies of the previous
+// indicator (one DMA FIFO per direction) and stall the launch pipeline behind them.
+__global__ void k_mail_bytes(unsigned char *__restrict__ dst_mapped, const unsigned char *__restrict__ src, int n) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dst_mapped[i] = src[i];
+  __threadfence_system();
+}
+
+// device twin of cco_partition_rows (cco_api.cu): contiguous item ranges of equal (products + 1 per row)
+__global__ void k_partition_rows(const long long *__restrict__ work_prefix, int32_t n_items, int32_t world, int32_t *bounds) {
+  const int r = threadIdx.x;
+  if (r > world) return;
+  if (r == 0) { bounds[0] = 0; return; }
+  if (r == world) { bounds[r] = n_items; return; }
+  const long long total = work_prefix[n_items] + n_items;
+  const long long target = (long long)((__int128)total * r / world);
+  int lo = 0, hi = n_items;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (work_prefix[mid] + mid < target) lo = mid + 1; else hi = mid;
+  }
+  bounds[r] = lo;
+}
+
 __global__ void k_max_i32(long long n, const int32_t *__restrict__ x, int32_t *__restrict__ out) {
   int32_t m = 0;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
