@@ -92,6 +92,10 @@ __device__ __forceinline__ uint32_t hash32(uint32_t x) {
 __device__ __forceinline__ double xlogx(long long x) {
   return x == 0 ? 0.0 : __dmul_rn((double)x, log((double)x));
 }
+// counts inside the row kernel are < 2^31 (n_rows < 2^31 is validated): the 32-bit conversion is exact and cheaper
+__device__ __forceinline__ double xlogx_u32(uint32_t x) {
+  return x == 0 ? 0.0 : __dmul_rn((double)x, log((double)x));
+}
 __device__ __forceinline__ double entropy2(long long a, long long b, bool varargs) {
   if (varargs) return __dsub_rn(xlogx(a + b), __dadd_rn(__dadd_rn(0.0, xlogx(a)), xlogx(b)));
   return __dsub_rn(__dsub_rn(xlogx(a + b), xlogx(a)), xlogx(b));
@@ -306,9 +310,10 @@ __global__ void k_bin_bounds(int32_t n_rows, const uint32_t *__restrict__ sorted
 // column, so it is evaluated once per column (same operations, same bits) instead of once per cell.
 // ------------------------------------------------------------------------------------------------
 struct __align__(16) ColTerm {
-  double col_e;
+  double col_e;     // entropy(cb, N - cb)
+  double x_cbm1;    // xLogX(cb - 1): the k21 term of every k11 == 1 cell of this column
   int32_t cb;
-  int32_t pad;
+  int32_t pad[3];
 };
 __global__ void k_col_terms(int32_t n_cols, const int32_t *__restrict__ marg, long long n_users, uint32_t flags,
                             ColTerm *__restrict__ out) {
@@ -317,8 +322,9 @@ __global__ void k_col_terms(int32_t n_cols, const int32_t *__restrict__ marg, lo
     long long cb = marg[i];
     ColTerm t;
     t.col_e = entropy2(cb, n_users - cb, varargs);
+    t.x_cbm1 = cb >= 1 ? xlogx(cb - 1) : 0.0;
     t.cb = (int32_t)cb;
-    t.pad = 0;
+    t.pad[0] = t.pad[1] = t.pad[2] = 0;
     out[i] = t;
   }
 }
@@ -676,9 +682,9 @@ __global__ void __launch_bounds__(GROUP == 32 ? 256 : GROUP) k_rows(const RowArg
           const uint32_t kf = k11 < (uint32_t)kDomLevels ? k11 : (uint32_t)kDomLevels;
           ++evaluated_local;
           const long long k21 = cb - k11, k22 = N - ra - cb + k11;
-          const double x11 = k11 < 32 ? x11tab[k11] : xlogx((long long)k11);
-          const double x12 = k11 < kX12N ? x12tab[k11] : xlogx(ra - k11);
-          const double x21 = xlogx(k21), x22 = xlogx(k22);
+          const double x11 = k11 < 32 ? x11tab[k11] : xlogx_u32(k11);
+          const double x12 = k11 < kX12N ? x12tab[k11] : xlogx_u32((uint32_t)(ra - k11));
+          const double x21 = k11 == 1 ? ct.x_cbm1 : xlogx_u32((uint32_t)k21), x22 = xlogx_u32((uint32_t)k22);
           double mat_e;
           if (varargs)
             mat_e = __dsub_rn(xN, __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(0.0, x11), x12), x21), x22));
