@@ -55,6 +55,10 @@ struct Nccl {
   int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
   int (*CommDestroy)(ncclComm_t) = nullptr;
   int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*Broadcast)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
   const char *(*GetErrorString)(int) = nullptr;
 };
 static Nccl g_nccl;
@@ -72,12 +76,16 @@ static int load_nccl() {
   SYM(CommInitRank, "ncclCommInitRank")
   SYM(CommDestroy, "ncclCommDestroy")
   SYM(AllReduce, "ncclAllReduce")
+  SYM(AllGather, "ncclAllGather")
+  SYM(Broadcast, "ncclBroadcast")
+  SYM(GroupStart, "ncclGroupStart")
+  SYM(GroupEnd, "ncclGroupEnd")
   SYM(GetErrorString, "ncclGetErrorString")
 #undef SYM
   g_nccl.h = h;
   return CCO_OK;
 }
-constexpr int kNcclInt32 = 2, kNcclSum = 0;  // ncclInt32, ncclSum (nccl.h enum values)
+constexpr int kNcclInt32 = 2, kNcclUint32 = 3, kNcclSum = 0;  // ncclInt32, ncclUint32, ncclSum (nccl.h enum values)
 
 }  // namespace cco
 
@@ -305,10 +313,66 @@ static int downsample_device(cco_ctx *c, Arena &ar, const DevRaw &raw, const int
   CK(cudaMemsetAsync(out->marg, 0, sizeof(int32_t) * std::max<int32_t>(raw.n_cols, 1), c->stream));
   CK(cudaMemsetAsync(kept + raw.n_rows, 0, 4, c->stream));
   int g = grid_for(raw.n_rows * kSG, 256, c->sm_count);
-  k_downsample_count<<<g, 256, 0, c->stream>>>(raw.n_rows, raw.rp, raw.col, raw_counts, m, seed, flags, kept, out->marg);
+  k_downsample_count<<<g, 256, 0, c->stream>>>(0, raw.n_rows, raw.rp, raw.col, raw_counts, m, seed, flags, kept, out->marg);
   CKR(exclusive_sum_u32(c, ar, kept, out->rp, raw.n_rows + 1));
-  k_downsample_write<<<g, 256, 0, c->stream>>>(raw.n_rows, raw.rp, raw.col, raw_counts, m, seed, flags, out->rp, out->col);
+  k_downsample_write<<<g, 256, 0, c->stream>>>(0, raw.n_rows, raw.rp, raw.col, raw_counts, m, seed, flags, out->rp, out->col);
   c->launches += 2;
+  CK(cudaGetLastError());
+  ar.release(kept);
+  return CCO_OK;
+}
+
+// Multi-GPU form of sampleDownAndBinarize: rank r samples only its block of users, the per-row kept counts are
+// all-gathered (so every rank derives the same row_ptr), each rank writes its block of the compacted column array at
+// its global offset and the blocks are exchanged with one grouped broadcast per rank over NVLink.  The post-sample
+// column marginals are then a local histogram of the gathered matrix.
+static int downsample_sharded(cco_ctx *c, Arena &ar, const DevRaw &raw, const int32_t *raw_counts, int32_t m, int32_t seed,
+                              uint32_t flags, DevMat *out) {
+  cudaStream_t s = c->stream;
+  const int W = c->world, r = c->rank;
+  const long long U = raw.n_rows;
+  const long long S = (U + W - 1) / W;
+  const long long u_lo = std::min<long long>((long long)r * S, U), u_hi = std::min<long long>(u_lo + S, U);
+  out->n_rows = U;
+  out->n_cols = raw.n_cols;
+  uint32_t *kept;
+  CKR(ar.alloc(&kept, (size_t)(W * S + 1)));
+  CKR(ar.alloc(&out->rp, U + 1));
+  CKR(ar.alloc(&out->marg, std::max<int32_t>(raw.n_cols, 1)));
+  CKR(ar.alloc(&out->col, std::max<long long>(raw.nnz, 1)));
+  CK(cudaMemsetAsync(out->marg, 0, sizeof(int32_t) * std::max<int32_t>(raw.n_cols, 1), s));
+  CK(cudaMemsetAsync(kept, 0, sizeof(uint32_t) * (size_t)(W * S + 1), s));
+  const int g = grid_for(std::max<long long>(u_hi - u_lo, 1) * kSG, 256, c->sm_count);
+  if (u_hi > u_lo) {
+    k_downsample_count<<<g, 256, 0, s>>>(u_lo, u_hi, raw.rp, raw.col, raw_counts, m, seed, flags, kept, nullptr);
+    c->launches++;
+  }
+  int rc = g_nccl.AllGather(kept + (size_t)r * S, kept, (size_t)S, kNcclUint32, c->comm, s);
+  if (rc != 0) return set_error(CCO_E_NCCL, "ncclAllGather: %s", g_nccl.GetErrorString(rc));
+  CKR(exclusive_sum_u32(c, ar, kept, out->rp, U + 1));
+  if (u_hi > u_lo) {
+    k_downsample_write<<<g, 256, 0, s>>>(u_lo, u_hi, raw.rp, raw.col, raw_counts, m, seed, flags, out->rp, out->col);
+    c->launches++;
+  }
+  std::vector<uint32_t> offs((size_t)W + 1, 0);
+  for (int q = 0; q <= W; ++q) CKR(mail_fetch(c, &offs[q], out->rp + std::min<long long>((long long)q * S, U), 4));
+  CKR(mail_wait(c));
+  g_nccl.GroupStart();
+  for (int q = 0; q < W; ++q) {
+    const size_t cnt = offs[q + 1] - offs[q];
+    if (cnt == 0) continue;
+    rc = g_nccl.Broadcast(out->col + offs[q], out->col + offs[q], cnt, kNcclInt32, q, c->comm, s);
+    if (rc != 0) {
+      g_nccl.GroupEnd();
+      return set_error(CCO_E_NCCL, "ncclBroadcast: %s", g_nccl.GetErrorString(rc));
+    }
+  }
+  rc = g_nccl.GroupEnd();
+  if (rc != 0) return set_error(CCO_E_NCCL, "ncclGroupEnd: %s", g_nccl.GetErrorString(rc));
+  if (offs[W] > 0) {
+    k_col_histogram_u32<<<grid_for(offs[W], 256, c->sm_count), 256, 0, s>>>(out->rp, out->rp + U, out->col, out->marg);
+    c->launches++;
+  }
   CK(cudaGetLastError());
   ar.release(kept);
   return CCO_OK;
@@ -807,8 +871,12 @@ static int train_dataset(cco_ctx *c, const cco_dataset *ds, const cco_indicator_
   }
   // sampleDownAndBinarize every matrix
   std::vector<DevMat> dm(n_mats);
-  for (int i = 0; i < n_mats; ++i)
-    CKR(downsample_device(c, ar, raw[i], raw_counts + col_off[i], params[i].max_interactions, seed, flags, &dm[i]));
+  for (int i = 0; i < n_mats; ++i) {
+    if (c->world > 1)
+      CKR(downsample_sharded(c, ar, raw[i], raw_counts + col_off[i], params[i].max_interactions, seed, flags, &dm[i]));
+    else
+      CKR(downsample_device(c, ar, raw[i], raw_counts + col_off[i], params[i].max_interactions, seed, flags, &dm[i]));
+  }
   // `drmA.t`
   const int32_t n_items_a = dm[0].n_cols;
   uint32_t *at_ptr, *cursor;

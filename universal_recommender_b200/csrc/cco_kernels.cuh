@@ -178,6 +178,24 @@ __global__ void k_col_histogram(long long row_begin, long long row_end, const lo
 }
 
 // perRowSampleRate of sampleDownAndBinarize (hoisted: once per row)
+// column histogram of the entries [*lo, *hi) of a column-index array (bounds read on the device, 32-bit offsets)
+__global__ void k_col_histogram_u32(const uint32_t *__restrict__ lo, const uint32_t *__restrict__ hi,
+                                    const int32_t *__restrict__ col, int32_t *__restrict__ counts) {
+  const long long s = *lo, e = *hi;
+  const int lane = threadIdx.x & 31;
+  for (long long q0 = s + blockIdx.x * (long long)blockDim.x + (threadIdx.x & ~31); q0 < e;
+       q0 += (long long)gridDim.x * blockDim.x) {
+    const long long q = q0 + lane;
+    const bool act = q < e;
+    const unsigned am = __ballot_sync(0xffffffffu, act);
+    if (act) {
+      const int32_t c = col[q];
+      const unsigned peers = __match_any_sync(am, c);
+      if ((__ffs(peers) - 1) == lane) atomicAdd(&counts[c], __popc(peers));
+    }
+  }
+}
+
 __device__ __forceinline__ double row_sample_rate(long long d, int32_t m, bool intdiv) {
   if (d <= 0) return 1.0;
   const long long md = d < m ? d : (long long)m;
@@ -194,12 +212,12 @@ __device__ __forceinline__ bool keep_entry(long long d, double row_rate, int32_t
 }
 
 // pass 1 of sampleDownAndBinarize: kept entries per row + post-sample column marginals
-__global__ void k_downsample_count(long long n_rows, const long long *__restrict__ rp, const int32_t *__restrict__ col,
+__global__ void k_downsample_count(long long row_begin, long long n_rows, const long long *__restrict__ rp, const int32_t *__restrict__ col,
                                    const int32_t *__restrict__ raw_counts, int32_t m, int32_t seed, uint32_t flags,
                                    uint32_t *__restrict__ kept_per_row, int32_t *__restrict__ new_counts) {
   const int lane = threadIdx.x % kSG;
   const unsigned sg_mask = ((1u << kSG) - 1u) << ((threadIdx.x & 31) / kSG * kSG);
-  long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / kSG;
+  long long row = row_begin + (blockIdx.x * (long long)blockDim.x + threadIdx.x) / kSG;  // rows [row_begin, n_rows)
   const long long stride = (long long)gridDim.x * blockDim.x / kSG;
   const bool intdiv = (flags & CCO_FLAG_ROWRATE_INTDIV) != 0;
   // all lanes of a sub-group share `row`, so loop trip counts are sub-group uniform
@@ -215,7 +233,7 @@ __global__ void k_downsample_count(long long n_rows, const long long *__restrict
         j = col[q];
         keep = keep_entry(d, row_rate, raw_counts[j], m, seed, (uint32_t)row, (uint32_t)j);
       }
-      if (keep) atomicAdd(&new_counts[j], 1);
+      if (keep && new_counts) atomicAdd(&new_counts[j], 1);
       kept += __popc(__ballot_sync(sg_mask, keep) & sg_mask);
     }
     if (lane == 0) kept_per_row[row] = kept;
@@ -223,13 +241,13 @@ __global__ void k_downsample_count(long long n_rows, const long long *__restrict
 }
 
 // pass 2: ordered compaction (ascending columns are preserved)
-__global__ void k_downsample_write(long long n_rows, const long long *__restrict__ rp, const int32_t *__restrict__ col,
+__global__ void k_downsample_write(long long row_begin, long long n_rows, const long long *__restrict__ rp, const int32_t *__restrict__ col,
                                    const int32_t *__restrict__ raw_counts, int32_t m, int32_t seed, uint32_t flags,
                                    const uint32_t *__restrict__ new_ptr, int32_t *__restrict__ new_col) {
   const int lane = threadIdx.x % kSG;
   const int sg_shift = (threadIdx.x & 31) / kSG * kSG;
   const unsigned sg_mask = ((1u << kSG) - 1u) << sg_shift;
-  long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / kSG;
+  long long row = row_begin + (blockIdx.x * (long long)blockDim.x + threadIdx.x) / kSG;  // rows [row_begin, n_rows)
   const long long stride = (long long)gridDim.x * blockDim.x / kSG;
   const bool intdiv = (flags & CCO_FLAG_ROWRATE_INTDIV) != 0;
   for (; row < n_rows; row += stride) {
