@@ -125,7 +125,7 @@ def cpu_arm(w: synth.Workload, args, sample: str):
     """Time the oracle (OpenMP, all host threads) on `sample` of the workload -> (events/s, cores, description, secs)."""
     from oracle import oracle as orc
     orc.build()
-    threads = orc.lib().orc_max_threads()
+    threads = host_threads()
     if sample == "full":
         sw, desc = w, f"full {w.name} workload"
     else:
@@ -151,7 +151,7 @@ def run_reference(args):
     # build the sample once, time W + K oracle runs on it
     from oracle import oracle as orc
     orc.build()
-    threads = orc.lib().orc_max_threads()
+    threads = host_threads()
     if sample == "full":
         sw = synth.make(args.workload)
         desc = f"full {args.workload} workload"
@@ -178,6 +178,14 @@ def run_reference(args):
                                      "reference's own Mahout-on-Spark path needs a JVM and is not runnable in this image"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def host_threads() -> int:
+    """All host threads this process may use -- NOT OMP_NUM_THREADS, which torchrun pins to 1 for its children."""
+    try:
+        return max(len(os.sched_getaffinity(0)), 1)
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 def auto_sample(workload: str) -> str:
@@ -299,7 +307,7 @@ def main():
     alg_total = sum_over_ranks(alg_bytes)
     rows_ms_max = max_over_ranks(rows_ms)
     achieved = alg_total / (rows_ms_max * 1e-3) / 1e9 / max(world, 1) if rows_ms_max > 0 else 0.0
-    n_row_launches = 5 * w.n_types * args.steps   # 5 work bins per indicator (the multi-pass bin is skipped when empty)
+    n_row_launches = 8 * w.n_types * args.steps   # 8 work-bin launches per indicator (empty bins exit immediately)
     roofline = {"bound": "hbm", "kernel": "k_rows (fused A'^T B' count + LLR + top-k; work-binned launches per indicator)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                 "traffic": ncu_traffic(args.workload, n_row_launches / max(args.steps * w.n_types, 1)), "algorithmic_bytes_per_launch": alg_total / max(world, 1) / n_row_launches,

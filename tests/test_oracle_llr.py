@@ -54,3 +54,26 @@ def test_entropy_order_variants_agree_to_roundoff(orc):
         a = orc.llr(k11, ra - k11, cb - k11, n - ra - cb + k11, 0)
         b = orc.llr(k11, ra - k11, cb - k11, n - ra - cb + k11, orc.FLAG_ENTROPY_VARARGS)
         assert a == pytest.approx(b, rel=1e-6, abs=1e-6)
+
+
+def test_dominance_property_behind_the_device_filter(orc):
+    """DESIGN.md 3.1 "dominance filter": on the positively associated side (rowA*colB < k11*N) the LLR grows with k11
+    and shrinks with colB, so a cell (k', c') with k' <= k and c' >= c never scores above (k, c)."""
+    import random
+    rng = random.Random(21)
+    checked = 0
+    for _ in range(4000):
+        n = 10 ** rng.randrange(3, 8)
+        ra = rng.randrange(1, min(600, n // 2))
+        c = rng.randrange(1, min(600, n // 2))
+        k = rng.randrange(1, min(ra, c) + 1)
+        kp = rng.randrange(1, k + 1)
+        cp = rng.randrange(c, min(c + 50, n - ra) + 1)
+        if kp > min(ra, cp) or not ra * cp < kp * n:          # the dominated cell must be on the positive side
+            continue
+        hi = orc.llr(k, ra - k, c - k, n - ra - c + k)
+        lo = orc.llr(kp, ra - kp, cp - kp, n - ra - cp + kp)
+        assert lo <= hi * (1 + 1e-12) + 1e-7, (n, ra, k, c, kp, cp)
+        if (kp, cp) != (k, c):
+            checked += 1
+    assert checked > 1000
