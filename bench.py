@@ -267,7 +267,8 @@ def main():
         ctx.train_dataset(ds, w.params, args.seed, flags | N.FLAG_RESULT_ON_DEVICE, copy_arrays=False)
     sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    if rank == 0:   # one NVML poller per job: eight of them contend for the driver lock and slow every rank's launches
+        sampler.start()
     ctx.timer_start()
     rows_ms, launches = 0.0, 0
     alg_bytes = 0.0

@@ -324,57 +324,66 @@ static int downsample_device(cco_ctx *c, Arena &ar, const DevRaw &raw, const int
 
 // Multi-GPU form of sampleDownAndBinarize: rank r samples only its block of users, the per-row kept counts are
 // all-gathered (so every rank derives the same row_ptr), each rank writes its block of the compacted column array at
-// its global offset and the blocks are exchanged with one grouped broadcast per rank over NVLink.  The post-sample
-// column marginals are then a local histogram of the gathered matrix.
-static int downsample_sharded(cco_ctx *c, Arena &ar, const DevRaw &raw, const int32_t *raw_counts, int32_t m, int32_t seed,
-                              uint32_t flags, DevMat *out) {
+// its global offset and the blocks are exchanged with grouped broadcasts over NVLink.  The post-sample column
+// marginals are then a local histogram of the gathered matrix.  All matrices go through phase 1 before the single
+// host synchronisation (block offsets), then ONE NCCL group moves every block of every matrix.
+static int downsample_sharded_all(cco_ctx *c, Arena &ar, const std::vector<DevRaw> &raw, const int32_t *raw_counts,
+                                  const std::vector<long long> &col_off, const cco_indicator_params_t *params, int32_t seed,
+                                  uint32_t flags, std::vector<DevMat> &dm) {
   cudaStream_t s = c->stream;
-  const int W = c->world, r = c->rank;
-  const long long U = raw.n_rows;
+  const int W = c->world, r = c->rank, n_mats = (int)raw.size();
+  const long long U = raw[0].n_rows;
   const long long S = (U + W - 1) / W;
   const long long u_lo = std::min<long long>((long long)r * S, U), u_hi = std::min<long long>(u_lo + S, U);
-  out->n_rows = U;
-  out->n_cols = raw.n_cols;
-  uint32_t *kept;
-  CKR(ar.alloc(&kept, (size_t)(W * S + 1)));
-  CKR(ar.alloc(&out->rp, U + 1));
-  CKR(ar.alloc(&out->marg, std::max<int32_t>(raw.n_cols, 1)));
-  CKR(ar.alloc(&out->col, std::max<long long>(raw.nnz, 1)));
-  CK(cudaMemsetAsync(out->marg, 0, sizeof(int32_t) * std::max<int32_t>(raw.n_cols, 1), s));
-  CK(cudaMemsetAsync(kept, 0, sizeof(uint32_t) * (size_t)(W * S + 1), s));
   const int g = grid_for(std::max<long long>(u_hi - u_lo, 1) * kSG, 256, c->sm_count);
-  if (u_hi > u_lo) {
-    k_downsample_count<<<g, 256, 0, s>>>(u_lo, u_hi, raw.rp, raw.col, raw_counts, m, seed, flags, kept, nullptr);
-    c->launches++;
+  std::vector<std::vector<uint32_t>> offs(n_mats, std::vector<uint32_t>((size_t)W + 1, 0));
+  for (int i = 0; i < n_mats; ++i) {
+    DevMat *out = &dm[i];
+    out->n_rows = U;
+    out->n_cols = raw[i].n_cols;
+    uint32_t *kept;
+    CKR(ar.alloc(&kept, (size_t)(W * S + 1)));
+    CKR(ar.alloc(&out->rp, U + 1));
+    CKR(ar.alloc(&out->marg, std::max<int32_t>(raw[i].n_cols, 1)));
+    CKR(ar.alloc(&out->col, std::max<long long>(raw[i].nnz, 1)));
+    CK(cudaMemsetAsync(out->marg, 0, sizeof(int32_t) * std::max<int32_t>(raw[i].n_cols, 1), s));
+    CK(cudaMemsetAsync(kept, 0, sizeof(uint32_t) * (size_t)(W * S + 1), s));
+    const int32_t m = params[i].max_interactions;
+    const int32_t *rc_i = raw_counts + col_off[i];
+    if (u_hi > u_lo) {
+      k_downsample_count<<<g, 256, 0, s>>>(u_lo, u_hi, raw[i].rp, raw[i].col, rc_i, m, seed, flags, kept, nullptr);
+      c->launches++;
+    }
+    int rc = g_nccl.AllGather(kept + (size_t)r * S, kept, (size_t)S, kNcclUint32, c->comm, s);
+    if (rc != 0) return set_error(CCO_E_NCCL, "ncclAllGather: %s", g_nccl.GetErrorString(rc));
+    CKR(exclusive_sum_u32(c, ar, kept, out->rp, U + 1));
+    if (u_hi > u_lo) {
+      k_downsample_write<<<g, 256, 0, s>>>(u_lo, u_hi, raw[i].rp, raw[i].col, rc_i, m, seed, flags, out->rp, out->col);
+      c->launches++;
+    }
+    for (int q = 0; q <= W; ++q) CKR(mail_fetch(c, &offs[i][q], out->rp + std::min<long long>((long long)q * S, U), 4));
+    ar.release(kept);
   }
-  int rc = g_nccl.AllGather(kept + (size_t)r * S, kept, (size_t)S, kNcclUint32, c->comm, s);
-  if (rc != 0) return set_error(CCO_E_NCCL, "ncclAllGather: %s", g_nccl.GetErrorString(rc));
-  CKR(exclusive_sum_u32(c, ar, kept, out->rp, U + 1));
-  if (u_hi > u_lo) {
-    k_downsample_write<<<g, 256, 0, s>>>(u_lo, u_hi, raw.rp, raw.col, raw_counts, m, seed, flags, out->rp, out->col);
-    c->launches++;
-  }
-  std::vector<uint32_t> offs((size_t)W + 1, 0);
-  for (int q = 0; q <= W; ++q) CKR(mail_fetch(c, &offs[q], out->rp + std::min<long long>((long long)q * S, U), 4));
   CKR(mail_wait(c));
   g_nccl.GroupStart();
-  for (int q = 0; q < W; ++q) {
-    const size_t cnt = offs[q + 1] - offs[q];
-    if (cnt == 0) continue;
-    rc = g_nccl.Broadcast(out->col + offs[q], out->col + offs[q], cnt, kNcclInt32, q, c->comm, s);
-    if (rc != 0) {
-      g_nccl.GroupEnd();
-      return set_error(CCO_E_NCCL, "ncclBroadcast: %s", g_nccl.GetErrorString(rc));
+  for (int i = 0; i < n_mats; ++i)
+    for (int q = 0; q < W; ++q) {
+      const size_t cnt = offs[i][q + 1] - offs[i][q];
+      if (cnt == 0) continue;
+      int rc = g_nccl.Broadcast(dm[i].col + offs[i][q], dm[i].col + offs[i][q], cnt, kNcclInt32, q, c->comm, s);
+      if (rc != 0) {
+        g_nccl.GroupEnd();
+        return set_error(CCO_E_NCCL, "ncclBroadcast: %s", g_nccl.GetErrorString(rc));
+      }
     }
-  }
-  rc = g_nccl.GroupEnd();
+  int rc = g_nccl.GroupEnd();
   if (rc != 0) return set_error(CCO_E_NCCL, "ncclGroupEnd: %s", g_nccl.GetErrorString(rc));
-  if (offs[W] > 0) {
-    k_col_histogram_u32<<<grid_for(offs[W], 256, c->sm_count), 256, 0, s>>>(out->rp, out->rp + U, out->col, out->marg);
-    c->launches++;
-  }
+  for (int i = 0; i < n_mats; ++i)
+    if (offs[i][W] > 0) {
+      k_col_histogram_u32<<<grid_for(offs[i][W], 256, c->sm_count), 256, 0, s>>>(dm[i].rp, dm[i].rp + U, dm[i].col, dm[i].marg);
+      c->launches++;
+    }
   CK(cudaGetLastError());
-  ar.release(kept);
   return CCO_OK;
 }
 
@@ -871,10 +880,10 @@ static int train_dataset(cco_ctx *c, const cco_dataset *ds, const cco_indicator_
   }
   // sampleDownAndBinarize every matrix
   std::vector<DevMat> dm(n_mats);
-  for (int i = 0; i < n_mats; ++i) {
-    if (c->world > 1)
-      CKR(downsample_sharded(c, ar, raw[i], raw_counts + col_off[i], params[i].max_interactions, seed, flags, &dm[i]));
-    else
+  if (c->world > 1) {
+    CKR(downsample_sharded_all(c, ar, raw, raw_counts, col_off, params, seed, flags, dm));
+  } else {
+    for (int i = 0; i < n_mats; ++i)
       CKR(downsample_device(c, ar, raw[i], raw_counts + col_off[i], params[i].max_interactions, seed, flags, &dm[i]));
   }
   // `drmA.t`
