@@ -1018,42 +1018,44 @@ int cco_create(const cco_config_t *cfg, cco_ctx_t **out) {
   if (p.major != 10)
     return set_error(CCO_E_CUDA, "device %d is sm_%d%d; this build contains sm_100a code only", cfg->device, p.major, p.minor);
   CK(cudaSetDevice(cfg->device));
+  if (cfg->world_size > 1 && !cfg->nccl_unique_id) return set_error(CCO_E_INVALID_ARG, "world_size > 1 needs nccl_unique_id");
   cco_ctx *c = new cco_ctx();
   c->device = cfg->device;
   c->rank = cfg->rank;
   c->world = cfg->world_size;
   c->sm_count = p.multiProcessorCount;
   c->smem_optin = p.sharedMemPerBlockOptin;
-  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-  for (auto &ev : c->ev) CK(cudaEventCreate(&ev));
-  for (auto &ev : c->tev) CK(cudaEventCreate(&ev));
-  for (auto &ev : c->copy_ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-  for (auto &st : c->bin_stream) CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-  for (auto &ev : c->bin_ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-  CK(cudaHostAlloc((void **)&c->mail_h, kMailBytes, cudaHostAllocMapped));
-  CK(cudaHostGetDevicePointer((void **)&c->mail_d, c->mail_h, 0));
-  cudaMemPool_t pool;
-  CK(cudaDeviceGetDefaultMemPool(&pool, cfg->device));
-  uint64_t thr = UINT64_MAX;
-  CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
-  if (c->world > 1) {
-    if (!cfg->nccl_unique_id) {
-      delete c;
-      return set_error(CCO_E_INVALID_ARG, "world_size > 1 needs nccl_unique_id");
+  // every failure below releases what was created so far (cco_destroy tolerates a half-built context)
+  auto init = [&]() -> int {
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (auto &ev : c->ev) CK(cudaEventCreate(&ev));
+    for (auto &ev : c->tev) CK(cudaEventCreate(&ev));
+    for (auto &ev : c->copy_ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (auto &st : c->bin_stream) CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    for (auto &ev : c->bin_ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CK(cudaHostAlloc((void **)&c->mail_h, kMailBytes, cudaHostAllocMapped));
+    CK(cudaHostGetDevicePointer((void **)&c->mail_d, c->mail_h, 0));
+    cudaMemPool_t pool;
+    CK(cudaDeviceGetDefaultMemPool(&pool, cfg->device));
+    uint64_t thr = UINT64_MAX;  // keep freed blocks: steady-state trains allocate nothing
+    CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    if (c->world > 1) {
+      CKR(load_nccl());
+      ncclUniqueId id;
+      memcpy(id.internal, cfg->nccl_unique_id, 128);
+      int rc = g_nccl.CommInitRank(&c->comm, c->world, id, c->rank);
+      if (rc != 0) return set_error(CCO_E_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString(rc));
     }
-    int r = load_nccl();
-    if (r != CCO_OK) {
-      delete c;
-      return r;
-    }
-    ncclUniqueId id;
-    memcpy(id.internal, cfg->nccl_unique_id, 128);
-    int rc = g_nccl.CommInitRank(&c->comm, c->world, id, c->rank);
-    if (rc != 0) {
-      delete c;
-      return set_error(CCO_E_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString(rc));
-    }
+    return CCO_OK;
+  };
+  const int st = init();
+  if (st != CCO_OK) {
+    char keep[sizeof g_err];
+    memcpy(keep, g_err, sizeof keep);   // cco_destroy must not clobber the message
+    cco_destroy(c);
+    memcpy(g_err, keep, sizeof keep);
+    return st;
   }
   *out = c;
   return CCO_OK;
@@ -1062,7 +1064,8 @@ int cco_create(const cco_config_t *cfg, cco_ctx_t **out) {
 int cco_destroy(cco_ctx_t *c) {
   if (!c) return CCO_OK;
   cudaSetDevice(c->device);
-  cudaStreamSynchronize(c->stream);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
   if (c->comm) g_nccl.CommDestroy(c->comm);
   for (auto &b : c->pinned) cudaFreeHost(b.p);
   if (c->mail_h) cudaFreeHost(c->mail_h);
@@ -1076,8 +1079,8 @@ int cco_destroy(cco_ctx_t *c) {
     if (st) cudaStreamDestroy(st);
   for (auto &ev : c->bin_ev)
     if (ev) cudaEventDestroy(ev);
-  cudaStreamDestroy(c->stream);
-  cudaStreamDestroy(c->copy_stream);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   delete c;
   return CCO_OK;
 }
