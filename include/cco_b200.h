@@ -118,7 +118,11 @@ typedef struct {
   int64_t distinct_cells[16];   /* per indicator: nnz(A'^T B') visited, this rank's rows */
   int64_t out_nnz[16];          /* per indicator: kept cells, this rank's rows */
   int64_t llr_evaluated[16];    /* per indicator: cells whose fp64 LLR was evaluated (rest: dominance-filtered) */
-  float ms_h2d, ms_prepare, ms_cooccurrence, ms_d2h, ms_total; /* CUDA-event times of this call */
+  /* CUDA-event times of this call.  ms_h2d: host->device copies (copy stream; overlaps ms_prepare in cco_train);
+   * ms_prepare: histogram + allreduce + sampleDownAndBinarize + transpose; ms_cooccurrence: all indicators incl.
+   * scheduling and result packing; ms_d2h: always 0 (the result copies overlap the next indicator on the copy
+   * stream and are inside ms_cooccurrence / ms_total); ms_total: the whole call on the launch stream. */
+  float ms_h2d, ms_prepare, ms_cooccurrence, ms_d2h, ms_total;
   float ms_indicator[16];       /* per indicator: row kernels only */
   int32_t n_kernel_launches;    /* kernels of this library launched by the call */
   int32_t n_mats;

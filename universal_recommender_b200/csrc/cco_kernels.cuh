@@ -2,12 +2,18 @@
 //
 // Reference semantics (what each stage replaces) -- Apache Mahout 0.13.0 SimilarityAnalysis,
 // called from /root/reference/src/main/scala/URAlgorithm.scala:323-329,343-346:
-//   H2 sampleDownAndBinarize  -> k_downsample_count / k_downsample_write
-//   H3 numNonZeroElementsPerColumn -> k_scan_rows (raw) + k_downsample_count (post-sample)
-//   `drmA.t`                  -> k_transpose_scatter
-//   H4 A'^T B' counts, H5 LLR, H6 top-k -> k_rows<> (one fused kernel, nothing materialised)
+//   input validation           -> k_check_rows; canonicalisation slow path k_expand_keys / k_unique_* / k_rowptr_from_keys
+//   H2 sampleDownAndBinarize   -> k_downsample_count / k_downsample_write (row ranges: whole matrix or a rank's user block)
+//   H3 numNonZeroElementsPerColumn -> k_col_histogram (raw, before the allreduce), k_downsample_count or
+//                                 k_col_histogram_u32 (post-sample)
+//   `drmA.t`                   -> k_transpose_scatter
+//   scheduling                 -> k_row_work, k_bin_bounds, k_partition_rows; per-column LLR constants k_col_terms
+//   H4 A'^T B' counts, H5 LLR, H6 top-k -> k_rows<GROUP, DENSE> (one fused kernel, nothing materialised)
+//   result assembly            -> k_len_to_i64, k_compact_rows; small device->host results k_mail_bytes
 //
-// Everything here is integer/byte work plus scalar fp64; no tensor cores (DESIGN.md "Roofline").
+// Everything here is integer/byte work plus scalar fp64; no tensor cores.  The accumulator, the
+// candidate buffer, the select histogram and the LLR tables of a row live in shared memory; B' and the per-column
+// terms are gathered from L2/HBM.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -47,7 +53,7 @@ struct RowArgs {
   int32_t keep_max;    // M: a prune keeps between top_k and max(M, top_k) candidates
   int32_t final_max;   // the final sort runs on at most this many candidates (next_pow2(top_k))
   int32_t group_smem_bytes;  // shared memory of one group (multiple of 16)
-  const struct ColTerm *col_terms;  // per column of B': {columnEntropy, colB}
+  const struct ColTerm *col_terms;  // per column of B': {columnEntropy, xLogX(colB - 1), colB}
   // outputs, strided
   int32_t out_stride;
   int32_t *out_col;
