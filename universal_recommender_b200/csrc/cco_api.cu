@@ -388,6 +388,7 @@ static int downsample_sharded_all(cco_ctx *c, Arena &ar, const std::vector<DevRa
 }
 
 // ---- row-kernel configurations -----------------------------------------------------------------
+
 struct BinCfg {
   int group;    // threads that own one row: 32 (warp), 256 or 1024 (whole CTA)
   int slots;    // table words per group
@@ -413,7 +414,9 @@ static int launch_rows_t(cco_ctx *c, const RowArgs &a, BinCfg &cfg, cudaStream_t
   void (*kern)(const RowArgs) = cfg.dense ? k_rows<GROUP, true> : k_rows<GROUP, false>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, CTA, cfg.smem));
-  kern<<<c->sm_count * std::max(occ, 1), CTA, cfg.smem, st>>>(a);
+  // 4 waves of CTAs over the work-sorted row list: a CTA that draws cheap rows retires early and the hardware
+  // scheduler backfills, which balances the tail better than one persistent wave (tools/tune_rows.py: -6 % at C3)
+  kern<<<c->sm_count * std::max(occ, 1) * 4, CTA, cfg.smem, st>>>(a);
   cfg.ctas_per_sm = occ;
   c->launches++;
   CK(cudaGetLastError());
@@ -436,13 +439,14 @@ static BinCfg make_cfg(cco_ctx *c, int group, int want_slots, int top_k, int n_c
   f.group = group;
   f.final_max = next_pow2(top_k);
   f.cbuf = next_pow2(top_k + std::max(group, 128) + (group == 32 ? 64 : 0));
+  if (group == 32 && top_k + 32 <= 96) f.cbuf = 128;  // small top_k: a 128-entry buffer doubles the warps per SM (-4 % at C3)
   f.keep_max = std::max(f.final_max, (f.cbuf - group) / 2);
   f.caux = group == 32 ? 0 : f.keep_max;
   size_t fixed = (size_t)(f.cbuf + f.caux) * 16 + 2 * 256 + 512 + 1024 + (size_t)(group / 32) * 256;  // candidates, x12/x11 tables, ctrl, histogram, queues
   size_t avail = (c->smem_optin - 1024) / groups;  // slack for static shared memory
   int max_slots = (int)((avail - fixed) / 4) & ~1023;
   f.slots = std::min(want_slots, max_slots);
-  f.cap = f.slots / 2;
+  f.cap = f.slots / 2;  // load factor <= 1/2: 2/3 and 3/4 are 8 % and 17 % slower (probe chains), tools/tune_rows.py
   f.dense = n_cols_b <= f.slots;
   f.region = (fixed + (size_t)f.slots * 4 + 15) & ~(size_t)15;
   f.smem = f.region * groups;
@@ -512,13 +516,15 @@ static int run_indicator(cco_ctx *c, Arena &ar, const uint32_t *at_ptr, const in
   const int k_eff = emit_all ? 1 : prm.top_k;
   const bool warp_ok = k_eff + 32 <= 256;  // warp-owned rows keep a 256-entry candidate buffer
   // Work bins, largest rows first.  {threads that own a row, table words, largest row work w the bin takes}.
-  // Bin 0 is the multi-pass bin (same config as bin 1).  Rows up to 2048 products are WARP-owned: no CTA barrier
+  // Bin 0 is the multi-pass bin (same config as bin 1).  Rows up to 1024 products are WARP-owned: no CTA barrier
   // anywhere in their count / compact / score / select pipeline (profiles/r01_k_rows_ncu_full.md: barriers cost the
   // CTA-owned bins 35-45 % of their warp time); larger rows need the table and the parallelism of a whole CTA.
   struct BinSpec { int group, slots; uint32_t max_w; };
   std::vector<BinSpec> spec = {{1024, 1 << 20, 0xffffffffu}, {1024, 1 << 20, 0xffffffffu}, {512, 16384, 8192u}, {256, 8192, 4096u}};
   if (warp_ok) {
-    spec.push_back({32, 4096, 2048u});
+    // rows of 1025..2048 products: a 128-thread CTA shares one 4096-word table (9 CTAs/SM) -- a warp-owned 4096-word
+    // table leaves only 10 warps per SM (tools/tune_rows.py: -4 % at C3); up to 1024 products rows are warp-owned
+    spec.push_back({128, 4096, 2048u});
     spec.push_back({32, 2048, 1024u});
     spec.push_back({32, 1024, 512u});
     spec.push_back({32, 512, 256u});
@@ -617,6 +623,7 @@ static int run_indicator(cco_ctx *c, Arena &ar, const uint32_t *at_ptr, const in
       ab.bin = b;
       ab.slots = cfgs[b].slots;
       ab.cap = cfgs[b].cap;
+      ab.tsize_x16 = 32;
       ab.cbuf = cfgs[b].cbuf;
       ab.caux = cfgs[b].caux;
       ab.keep_max = cfgs[b].keep_max;

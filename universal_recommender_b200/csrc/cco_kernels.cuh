@@ -48,6 +48,7 @@ struct RowArgs {
   int32_t count_bits;  // packed hash word = (key << count_bits) | count
   int32_t slots;       // hash/dense table words in shared memory
   int32_t cap;         // max distinct keys per pass for hashed rows (load-factor bound)
+  int32_t tsize_x16;   // table words per expected distinct key, in sixteenths (32 = load factor 1/2)
   int32_t cbuf;        // candidate buffer entries per group (power of two, >= top_k + GROUP)
   int32_t caux;        // scratch entries for the out-of-place compaction of the radix select (0 for warps)
   int32_t keep_max;    // M: a prune keeps between top_k and max(M, top_k) candidates
@@ -565,7 +566,7 @@ __global__ void __launch_bounds__(GROUP == 32 ? 256 : GROUP) k_rows(const RowArg
       const uint32_t dbound = w < (uint32_t)a.n_cols_b ? w : (uint32_t)a.n_cols_b;
       n_pass = (dbound + (uint32_t)a.cap - 1u) / (uint32_t)a.cap;
       if (n_pass == 0) n_pass = 1;
-      tsize = n_pass > 1 ? (uint32_t)a.slots : min((uint32_t)a.slots, max(2u * dbound, 64u));
+      tsize = n_pass > 1 ? (uint32_t)a.slots : min((uint32_t)a.slots, max((dbound * (uint32_t)a.tsize_x16) >> 4, 64u));
       tsize = min((uint32_t)a.slots, (tsize + 32u * NW - 1u) / (32u * NW) * (32u * NW));
     }
     group_sync<GROUP>();  // previous row fully done with shared memory
