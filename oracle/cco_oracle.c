@@ -537,6 +537,83 @@ done:
   return rc;
 }
 
+/* ---------------------------------------------------------------------------------------------
+ * orc_ingest: Preparator.prepare (Preparator.scala:44-87) with IndexedDatasetSpark.apply(elements, minEventsPerUser)
+ * (:102-158, user filter counting duplicate events :129-132) and apply(elements, existingRowIDs) (:160-214, events
+ * of unknown users dropped :175-178, item ids from the surviving events :184, setQuick dedup :201-208).
+ * ------------------------------------------------------------------------------------------- */
+void orc_free_ingested(orc_ingested_t *r) {
+  if (!r) return;
+  free(r->row_ptr);
+  free(r->col_idx);
+  free(r->item_map);
+  memset(r, 0, sizeof *r);
+}
+
+int orc_ingest(int n_types, const orc_events_t *ev, int64_t n_users_raw, int32_t min_events_per_user, int32_t *user_map,
+               orc_ingested_t *out) {
+  if (n_types < 1 || !ev || !user_map || !out) FAIL("bad argument");
+  if (n_users_raw < 0 || n_users_raw > 0x7fffffff) FAIL("n_users_raw out of range");
+  memset(out, 0, sizeof(orc_ingested_t) * (size_t)n_types);
+  for (int t = 0; t < n_types; ++t)
+    for (int64_t i = 0; i < ev[t].n_events; ++i) {
+      if (ev[t].user[i] < 0 || ev[t].user[i] >= n_users_raw) FAIL("type %d: user id out of range at %lld", t, (long long)i);
+      if (ev[t].item[i] < 0 || ev[t].item[i] >= ev[t].n_items_raw) FAIL("type %d: item id out of range at %lld", t, (long long)i);
+    }
+  /* user dictionary from the primary events (duplicates count) */
+  int64_t *cnt = (int64_t *)calloc((size_t)(n_users_raw > 0 ? n_users_raw : 1), sizeof(int64_t));
+  if (!cnt) FAIL("out of memory");
+  for (int64_t i = 0; i < ev[0].n_events; ++i) cnt[ev[0].user[i]]++;
+  const int64_t need = min_events_per_user > 1 ? min_events_per_user : 1;
+  int32_t n_users = 0;
+  for (int64_t u = 0; u < n_users_raw; ++u) user_map[u] = cnt[u] >= need ? n_users++ : -1;
+  free(cnt);
+  for (int t = 0; t < n_types; ++t) {
+    orc_ingested_t *o = &out[t];
+    const int32_t ni = ev[t].n_items_raw;
+    o->item_map = (int32_t *)malloc(sizeof(int32_t) * (size_t)(ni > 0 ? ni : 1));
+    o->row_ptr = (int64_t *)calloc((size_t)n_users + 1, sizeof(int64_t));
+    if (!o->item_map || !o->row_ptr) FAIL("out of memory");
+    /* item dictionary: items with a surviving event */
+    for (int32_t j = 0; j < ni; ++j) o->item_map[j] = -1;
+    for (int64_t i = 0; i < ev[t].n_events; ++i)
+      if (user_map[ev[t].user[i]] >= 0) o->item_map[ev[t].item[i]] = 0;
+    int32_t n_items = 0;
+    for (int32_t j = 0; j < ni; ++j)
+      if (o->item_map[j] == 0) o->item_map[j] = n_items++;
+    o->n_rows = n_users;
+    o->n_cols = n_items;
+    /* bucket the surviving events by user, then sort + dedup each row */
+    for (int64_t i = 0; i < ev[t].n_events; ++i) {
+      int32_t r = user_map[ev[t].user[i]];
+      if (r >= 0) o->row_ptr[r + 1]++;
+    }
+    for (int32_t r = 0; r < n_users; ++r) o->row_ptr[r + 1] += o->row_ptr[r];
+    int64_t kept = o->row_ptr[n_users];
+    int32_t *tmp = (int32_t *)malloc(sizeof(int32_t) * (size_t)(kept > 0 ? kept : 1));
+    int64_t *cur = (int64_t *)malloc(sizeof(int64_t) * ((size_t)n_users + 1));
+    o->col_idx = (int32_t *)malloc(sizeof(int32_t) * (size_t)(kept > 0 ? kept : 1));
+    if (!tmp || !cur || !o->col_idx) FAIL("out of memory");
+    memcpy(cur, o->row_ptr, sizeof(int64_t) * ((size_t)n_users + 1));
+    for (int64_t i = 0; i < ev[t].n_events; ++i) {
+      int32_t r = user_map[ev[t].user[i]];
+      if (r >= 0) tmp[cur[r]++] = o->item_map[ev[t].item[i]];
+    }
+    int64_t w = 0;
+    for (int32_t r = 0; r < n_users; ++r) {
+      int64_t s = o->row_ptr[r], e = o->row_ptr[r + 1];
+      qsort(tmp + s, (size_t)(e - s), sizeof(int32_t), cmp_i32);
+      o->row_ptr[r] = w;
+      for (int64_t i = s; i < e; ++i)
+        if (i == s || tmp[i] != tmp[i - 1]) o->col_idx[w++] = tmp[i];
+    }
+    o->row_ptr[n_users] = w;
+    free(tmp);
+    free(cur);
+  }
+  return 0;
+}
+
 void orc_free_result(orc_result_t *r) {
   if (!r) return;
   free(r->row_ptr);
