@@ -442,7 +442,7 @@ static BinCfg make_cfg(cco_ctx *c, int group, int want_slots, int top_k, int n_c
   if (group == 32 && top_k + 32 <= 96) f.cbuf = 128;  // small top_k: a 128-entry buffer doubles the warps per SM (-4 % at C3)
   f.keep_max = std::max(f.final_max, (f.cbuf - group) / 2);
   f.caux = group == 32 ? 0 : f.keep_max;
-  size_t fixed = (size_t)(f.cbuf + f.caux) * 16 + 2 * 256 + 512 + 1024 + (size_t)(group / 32) * 256;  // candidates, x12/x11 tables, ctrl, histogram, queues
+  size_t fixed = (size_t)(f.cbuf + f.caux) * 16 + 2 * 256 + 512 + 1024 + (size_t)(group / 32) * 256 + 2048;  // candidates, x12/x11 tables, ctrl, histogram, queues, level-1 cut histogram
   size_t avail = (c->smem_optin - 1024) / groups;  // slack for static shared memory
   int max_slots = (int)((avail - fixed) / 4) & ~1023;
   f.slots = std::min(want_slots, max_slots);

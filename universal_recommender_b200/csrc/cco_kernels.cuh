@@ -500,6 +500,7 @@ __device__ int reduce_candidates(uint4 *tk, uint4 *aux, int n, int k, int M, int
   return kept;
 }
 
+constexpr int kCutBins = 1024;  // level-1 integer cut: colB histogram bins (cells with colB >= kCutBins are never cut)
 constexpr int kDomLevels = 15;  // dominance filter keeps cfail[1..15] in ctrl[41..55]
 constexpr int kX12N = 31;  // x12tab[j] = xLogX(ra - j) for j < 31; x12tab[31] = xLogX(N - ra)
 
@@ -542,7 +543,8 @@ __global__ void __launch_bounds__(GROUP == 32 ? 256 : GROUP) k_rows(const RowArg
   int *ctrl = reinterpret_cast<int *>(x11tab + 32);  // [0] ncand [1] have_thr [4..7] threshold entry [16..27] select state [40..55] dominance frontier [64..64+NW) per-warp list sizes
   int *hist = ctrl + 128;                                     // 256 bins of the radix select
   uint32_t *wqueue = reinterpret_cast<uint32_t *>(hist + 256);  // NW * 64 queued cells awaiting evaluation
-  uint32_t *table = wqueue + NW * 64;
+  uint32_t *h1 = wqueue + NW * 64;   // kCutBins/2 words: u16 histogram of colB over the strongly positive k11 == 1 cells
+  uint32_t *table = h1 + kCutBins / 2;
   volatile int *vctrl = ctrl;
 
   const int row_begin = a.bin_bounds[a.bin], row_end = a.bin_bounds[a.bin + 1];
@@ -661,6 +663,56 @@ __global__ void __launch_bounds__(GROUP == 32 ? 256 : GROUP) k_rows(const RowArg
         group_sync<GROUP>();
         continue;
       }
+      // ---- level-1 integer cut (exact) ---------------------------------------------------------------
+      // On the strongly positive side (2*rowA*colB < k11*N) the LLR of k11 == 1 cells is strictly decreasing in colB, so
+      // the smallest colB c1 with >= top_k such cells at or below it bounds the row's k-th best from below: k11 == 1 cells
+      // with colB > c1 can never be kept and are dropped by an integer compare in the filter stage.
+      int cut1 = 0x7fffffff;
+      if (a.row_work[item] < 65536u) {   // u16 bins cannot overflow
+        for (int i = gtid; i < kCutBins / 2; i += GROUP) h1[i] = 0u;
+        group_sync<GROUP>();
+        for (uint32_t q0 = 0; q0 < n_mine; q0 += 32) {
+          const uint32_t q = q0 + lane;
+          if (q < n_mine) {
+            const uint32_t word = table[seg_lo + q];
+            const uint32_t b = word >> cbits;
+            if ((word & cmask) == 1u && !(a.self && (int)b == item)) {
+              const uint32_t cb = (uint32_t)a.marg_b[b];
+              if (cb < (uint32_t)kCutBins && 2ull * (unsigned long long)ra * cb < (unsigned long long)N)
+                atomicAdd(&h1[cb >> 1], 1u << (16u * (cb & 1u)));
+            }
+          }
+        }
+        group_sync<GROUP>();
+        if (gtid < 32) {
+          // lane l owns bins [32 l, 32 l + 32): 16 words
+          uint32_t sum = 0;
+          for (int wi = 0; wi < 16; ++wi) { const uint32_t v = h1[gtid * 16 + wi]; sum += (v & 0xffffu) + (v >> 16); }
+          uint32_t incl = sum;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (gtid >= d) incl += v;
+          }
+          const uint32_t excl = incl - sum;
+          int found = 0x7fffffff;
+          if (excl < (uint32_t)a.top_k && incl >= (uint32_t)a.top_k) {
+            uint32_t run = excl;
+            for (int wi = 0; wi < 16 && found == 0x7fffffff; ++wi) {
+              const uint32_t v = h1[gtid * 16 + wi];
+              run += v & 0xffffu;
+              if (run >= (uint32_t)a.top_k) { found = gtid * 32 + 2 * wi; break; }
+              run += v >> 16;
+              if (run >= (uint32_t)a.top_k) { found = gtid * 32 + 2 * wi + 1; break; }
+            }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) found = min(found, __shfl_xor_sync(0xffffffffu, found, o));
+          if (gtid == 0) ctrl[9] = found;
+        }
+        group_sync<GROUP>();
+        cut1 = vctrl[9];
+      }
       // ---- score + select -----------------------------------------------------------------------------------
       const double x_ra = x12tab[0], x_nra = x12tab[kX12N];
       const double row_e = varargs ? __dsub_rn(xN, __dadd_rn(__dadd_rn(0.0, x_ra), x_nra))
@@ -687,6 +739,8 @@ __global__ void __launch_bounds__(GROUP == 32 ? 256 : GROUP) k_rows(const RowArg
               const long long cb = a.marg_b[b];
               const bool pos_side = (unsigned long long)ra * (unsigned long long)cb < (unsigned long long)k11 * (unsigned long long)N;
               surv = !(pos_side && k11 <= (uint32_t)kDomLevels && (int)cb >= vctrl[40 + k11]);
+              if (k11 == 1u && (int)cb > cut1 && cb < kCutBins && 2ull * (unsigned long long)ra * (unsigned long long)cb < (unsigned long long)N)
+                surv = false;   // beyond the level-1 integer cut
             }
           }
           const unsigned m = __ballot_sync(0xffffffffu, surv);
