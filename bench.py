@@ -171,7 +171,7 @@ def run_reference(args):
     v = sw.n_events / dt
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "int32 counts + f64 LLR", "data": "synthetic",
+            "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
             "config": {"workload": workload_desc(args.workload), "sample": desc},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc,
                              "note": "CPU restatement of Mahout 0.13.0 SimilarityAnalysis (oracle/cco_oracle.c, OpenMP); the "
@@ -322,7 +322,7 @@ def main():
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "int32 counts + f64 LLR", "data": "synthetic",
+            "dtype": "int32+f64", "data": "synthetic",
             "config": {"workload": workload_desc(args.workload), "parallelism": f"item-row sharding x{world}",
                        "l2": "inputs (%.0f MB) larger than the 126 MB L2; no explicit flush" % (h2d_bytes / 1e6)
                        if h2d_bytes > 126e6 else "inputs fit L2 (%.0f MB); no explicit flush" % (h2d_bytes / 1e6),

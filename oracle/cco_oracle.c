@@ -127,12 +127,23 @@ static int validate(const orc_csr_t *m) {
   if (m->n_rows < 0 || m->n_rows > 0x7fffffff) FAIL("n_rows out of range (Mahout row keys are Int)");
   if (m->n_cols < 0) FAIL("n_cols < 0");
   if (m->row_ptr[0] != 0) FAIL("row_ptr[0] != 0");
+  int64_t bad_row = -1, bad_idx = -1;
+#pragma omp parallel for schedule(static, 65536)
   for (int64_t r = 0; r < m->n_rows; ++r)
-    if (m->row_ptr[r + 1] < m->row_ptr[r]) FAIL("row_ptr not monotone at row %lld", (long long)r);
+    if (m->row_ptr[r + 1] < m->row_ptr[r]) {
+#pragma omp critical
+      bad_row = r;
+    }
+  if (bad_row >= 0) FAIL("row_ptr not monotone at row %lld", (long long)bad_row);
   int64_t nnz = m->row_ptr[m->n_rows];
   if (nnz > 0 && !m->col_idx) FAIL("null col_idx");
+#pragma omp parallel for schedule(static, 65536)
   for (int64_t i = 0; i < nnz; ++i)
-    if (m->col_idx[i] < 0 || m->col_idx[i] >= m->n_cols) FAIL("col_idx out of range at %lld", (long long)i);
+    if (m->col_idx[i] < 0 || m->col_idx[i] >= m->n_cols) {
+#pragma omp critical
+      bad_idx = i;
+    }
+  if (bad_idx >= 0) FAIL("col_idx out of range at %lld", (long long)bad_idx);
   return 0;
 }
 
@@ -142,6 +153,19 @@ int orc_canonicalize(const orc_csr_t *in, int64_t **row_ptr, int32_t **col_idx) 
   int64_t *rp = (int64_t *)malloc(sizeof(int64_t) * (size_t)(in->n_rows + 1));
   int32_t *ci = (int32_t *)malloc(sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1));
   if (!rp || !ci) FAIL("out of memory");
+  /* fast path: every row already strictly ascending (what Preparator-built matrices look like after a sort) */
+  int all_sorted = 1;
+#pragma omp parallel for schedule(static, 4096) reduction(&& : all_sorted)
+  for (int64_t r = 0; r < in->n_rows; ++r)
+    for (int64_t i = in->row_ptr[r] + 1; i < in->row_ptr[r + 1]; ++i)
+      if (in->col_idx[i] <= in->col_idx[i - 1]) all_sorted = 0;
+  if (all_sorted) {
+    memcpy(rp, in->row_ptr, sizeof(int64_t) * (size_t)(in->n_rows + 1));
+    if (nnz > 0) memcpy(ci, in->col_idx, sizeof(int32_t) * (size_t)nnz);
+    *row_ptr = rp;
+    *col_idx = ci;
+    return 0;
+  }
   int64_t w = 0;
   rp[0] = 0;
   for (int64_t r = 0; r < in->n_rows; ++r) {
@@ -173,6 +197,16 @@ int orc_canonicalize(const orc_csr_t *in, int64_t **row_ptr, int32_t **col_idx) 
  *   perThingSampleRate = min(m, c_j) / c_j     (c_j Double -> real division)
  *   keep (r, j) iff random.nextDouble() <= min(perRowSampleRate, perThingSampleRate); value 1
  * ------------------------------------------------------------------------------------------- */
+static inline int keep_entry(const orc_csr_t *in, const int32_t *cc, int64_t r, int64_t d, double row_rate, int64_t i,
+                             int32_t m, int32_t seed) {
+  int32_t j = in->col_idx[i];
+  double c = (double)cc[j];
+  double col_rate = (c < (double)m ? c : (double)m) / c;
+  double rate = row_rate < col_rate ? row_rate : col_rate;
+  (void)d;
+  return orc_u01(orc_hash64(seed, r, j)) <= rate;
+}
+
 int orc_downsample(const orc_csr_t *in, int32_t m, int32_t seed, int flags, int64_t **row_ptr,
                    int32_t **col_idx, int32_t *raw_col_counts, int32_t *new_col_counts) {
   if (m < 1) FAIL("max_interactions must be >= 1");
@@ -184,27 +218,35 @@ int orc_downsample(const orc_csr_t *in, int32_t m, int32_t seed, int flags, int6
   for (int64_t i = 0; i < nnz; ++i) cc[in->col_idx[i]]++;
   if (raw_col_counts) memcpy(raw_col_counts, cc, sizeof(int32_t) * (size_t)in->n_cols);
   if (new_col_counts) memset(new_col_counts, 0, sizeof(int32_t) * (size_t)in->n_cols);
-  int64_t w = 0;
+  /* pass 1 (parallel over rows): kept entries per row; the keep decision is a pure function of (seed, row, col) */
   rp[0] = 0;
+#pragma omp parallel for schedule(static, 4096)
   for (int64_t r = 0; r < in->n_rows; ++r) {
-    int64_t s = in->row_ptr[r], e = in->row_ptr[r + 1];
-    int64_t d = e - s;
+    int64_t s = in->row_ptr[r], e = in->row_ptr[r + 1], d = e - s, kept = 0;
     double row_rate = 1.0;
     if (d > 0) {
       int64_t md = d < m ? d : m;
       row_rate = (flags & ORC_FLAG_ROWRATE_INTDIV) ? (double)(md / d) : (double)md / (double)d;
     }
-    for (int64_t i = s; i < e; ++i) {
-      int32_t j = in->col_idx[i];
-      double c = (double)cc[j];
-      double col_rate = (c < (double)m ? c : (double)m) / c;
-      double rate = row_rate < col_rate ? row_rate : col_rate;
-      if (orc_u01(orc_hash64(seed, r, j)) <= rate) {
-        ci[w++] = j;
-        if (new_col_counts) new_col_counts[j]++;
-      }
+    for (int64_t i = s; i < e; ++i) kept += keep_entry(in, cc, r, d, row_rate, i, m, seed);
+    rp[r + 1] = kept;
+  }
+  for (int64_t r = 0; r < in->n_rows; ++r) rp[r + 1] += rp[r];
+  /* pass 2 (parallel over rows): ordered write */
+#pragma omp parallel for schedule(static, 4096)
+  for (int64_t r = 0; r < in->n_rows; ++r) {
+    int64_t s = in->row_ptr[r], e = in->row_ptr[r + 1], d = e - s, w = rp[r];
+    double row_rate = 1.0;
+    if (d > 0) {
+      int64_t md = d < m ? d : m;
+      row_rate = (flags & ORC_FLAG_ROWRATE_INTDIV) ? (double)(md / d) : (double)md / (double)d;
     }
-    rp[r + 1] = w;
+    for (int64_t i = s; i < e; ++i)
+      if (keep_entry(in, cc, r, d, row_rate, i, m, seed)) ci[w++] = in->col_idx[i];
+  }
+  if (new_col_counts) {
+    int64_t total = rp[in->n_rows];
+    for (int64_t i = 0; i < total; ++i) new_col_counts[ci[i]]++;
   }
   free(cc);
   *row_ptr = rp;
@@ -493,6 +535,83 @@ done:
   if (rc)
     for (int i = 0; i < n_mats; ++i) orc_free_result(&results[i]);
   return rc;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * orc_ingest: Preparator.prepare (Preparator.scala:44-87) with IndexedDatasetSpark.apply(elements, minEventsPerUser)
+ * (:102-158, user filter counting duplicate events :129-132) and apply(elements, existingRowIDs) (:160-214, events
+ * of unknown users dropped :175-178, item ids from the surviving events :184, setQuick dedup :201-208).
+ * ------------------------------------------------------------------------------------------- */
+void orc_free_ingested(orc_ingested_t *r) {
+  if (!r) return;
+  free(r->row_ptr);
+  free(r->col_idx);
+  free(r->item_map);
+  memset(r, 0, sizeof *r);
+}
+
+int orc_ingest(int n_types, const orc_events_t *ev, int64_t n_users_raw, int32_t min_events_per_user, int32_t *user_map,
+               orc_ingested_t *out) {
+  if (n_types < 1 || !ev || !user_map || !out) FAIL("bad argument");
+  if (n_users_raw < 0 || n_users_raw > 0x7fffffff) FAIL("n_users_raw out of range");
+  memset(out, 0, sizeof(orc_ingested_t) * (size_t)n_types);
+  for (int t = 0; t < n_types; ++t)
+    for (int64_t i = 0; i < ev[t].n_events; ++i) {
+      if (ev[t].user[i] < 0 || ev[t].user[i] >= n_users_raw) FAIL("type %d: user id out of range at %lld", t, (long long)i);
+      if (ev[t].item[i] < 0 || ev[t].item[i] >= ev[t].n_items_raw) FAIL("type %d: item id out of range at %lld", t, (long long)i);
+    }
+  /* user dictionary from the primary events (duplicates count) */
+  int64_t *cnt = (int64_t *)calloc((size_t)(n_users_raw > 0 ? n_users_raw : 1), sizeof(int64_t));
+  if (!cnt) FAIL("out of memory");
+  for (int64_t i = 0; i < ev[0].n_events; ++i) cnt[ev[0].user[i]]++;
+  const int64_t need = min_events_per_user > 1 ? min_events_per_user : 1;
+  int32_t n_users = 0;
+  for (int64_t u = 0; u < n_users_raw; ++u) user_map[u] = cnt[u] >= need ? n_users++ : -1;
+  free(cnt);
+  for (int t = 0; t < n_types; ++t) {
+    orc_ingested_t *o = &out[t];
+    const int32_t ni = ev[t].n_items_raw;
+    o->item_map = (int32_t *)malloc(sizeof(int32_t) * (size_t)(ni > 0 ? ni : 1));
+    o->row_ptr = (int64_t *)calloc((size_t)n_users + 1, sizeof(int64_t));
+    if (!o->item_map || !o->row_ptr) FAIL("out of memory");
+    /* item dictionary: items with a surviving event */
+    for (int32_t j = 0; j < ni; ++j) o->item_map[j] = -1;
+    for (int64_t i = 0; i < ev[t].n_events; ++i)
+      if (user_map[ev[t].user[i]] >= 0) o->item_map[ev[t].item[i]] = 0;
+    int32_t n_items = 0;
+    for (int32_t j = 0; j < ni; ++j)
+      if (o->item_map[j] == 0) o->item_map[j] = n_items++;
+    o->n_rows = n_users;
+    o->n_cols = n_items;
+    /* bucket the surviving events by user, then sort + dedup each row */
+    for (int64_t i = 0; i < ev[t].n_events; ++i) {
+      int32_t r = user_map[ev[t].user[i]];
+      if (r >= 0) o->row_ptr[r + 1]++;
+    }
+    for (int32_t r = 0; r < n_users; ++r) o->row_ptr[r + 1] += o->row_ptr[r];
+    int64_t kept = o->row_ptr[n_users];
+    int32_t *tmp = (int32_t *)malloc(sizeof(int32_t) * (size_t)(kept > 0 ? kept : 1));
+    int64_t *cur = (int64_t *)malloc(sizeof(int64_t) * ((size_t)n_users + 1));
+    o->col_idx = (int32_t *)malloc(sizeof(int32_t) * (size_t)(kept > 0 ? kept : 1));
+    if (!tmp || !cur || !o->col_idx) FAIL("out of memory");
+    memcpy(cur, o->row_ptr, sizeof(int64_t) * ((size_t)n_users + 1));
+    for (int64_t i = 0; i < ev[t].n_events; ++i) {
+      int32_t r = user_map[ev[t].user[i]];
+      if (r >= 0) tmp[cur[r]++] = o->item_map[ev[t].item[i]];
+    }
+    int64_t w = 0;
+    for (int32_t r = 0; r < n_users; ++r) {
+      int64_t s = o->row_ptr[r], e = o->row_ptr[r + 1];
+      qsort(tmp + s, (size_t)(e - s), sizeof(int32_t), cmp_i32);
+      o->row_ptr[r] = w;
+      for (int64_t i = s; i < e; ++i)
+        if (i == s || tmp[i] != tmp[i - 1]) o->col_idx[w++] = tmp[i];
+    }
+    o->row_ptr[n_users] = w;
+    free(tmp);
+    free(cur);
+  }
+  return 0;
 }
 
 void orc_free_result(orc_result_t *r) {

@@ -89,6 +89,32 @@ int orc_cooccurrence(const orc_csr_t *a, const orc_csr_t *b, int64_t **row_ptr, 
 int orc_train(int n_mats, const orc_csr_t *mats, const orc_params_t *params, int32_t seed, int flags,
               int n_threads, orc_result_t *results);
 
+/* ---- next row: the ingest that sits right before the boundary --------------------------------------
+ * Preparator.prepare + IndexedDatasetSpark.apply (Preparator.scala:44-87, 100-216) on integer-tokenised events.
+ * Type 0 is the primary event.  The user dictionary is fixed by the primary events (users with at least
+ * min_events_per_user primary events, duplicates counted; min 0/1 = every user with a primary event); every type is
+ * restricted to those users; each type's item dictionary holds only items that still have an event; duplicates collapse.
+ * Dictionary order here: ascending raw id (Mahout's is the arbitrary order of distinct().collect()). */
+typedef struct {
+  int64_t n_events;
+  const int64_t *user; /* raw user id in [0, n_users_raw) */
+  const int32_t *item; /* raw item id in [0, n_items_raw) */
+  int32_t n_items_raw;
+} orc_events_t;
+
+typedef struct {
+  int64_t n_rows;    /* = size of the user dictionary, equal for every type */
+  int32_t n_cols;    /* = size of this type's item dictionary */
+  int64_t *row_ptr;  /* binary CSR, columns ascending */
+  int32_t *col_idx;
+  int32_t *item_map; /* [n_items_raw]: new column id or -1 */
+} orc_ingested_t;
+
+/* user_map: caller-provided [n_users_raw], receives the new row id or -1.  out: caller-provided [n_types]. */
+int orc_ingest(int n_types, const orc_events_t *ev, int64_t n_users_raw, int32_t min_events_per_user, int32_t *user_map,
+               orc_ingested_t *out);
+void orc_free_ingested(orc_ingested_t *r);
+
 void orc_free_result(orc_result_t *r);
 void orc_free(void *p);
 int orc_max_threads(void);

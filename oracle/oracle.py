@@ -39,6 +39,15 @@ class _Result(C.Structure):
                 ("nnz_a", C.c_int64), ("nnz_b", C.c_int64)]
 
 
+class _Events(C.Structure):
+    _fields_ = [("n_events", C.c_int64), ("user", C.POINTER(C.c_int64)), ("item", C.POINTER(C.c_int32)), ("n_items_raw", C.c_int32)]
+
+
+class _Ingested(C.Structure):
+    _fields_ = [("n_rows", C.c_int64), ("n_cols", C.c_int32), ("row_ptr", C.POINTER(C.c_int64)),
+                ("col_idx", C.POINTER(C.c_int32)), ("item_map", C.POINTER(C.c_int32))]
+
+
 def build(force: bool = False) -> str:
     """Compile the oracle with the committed Makefile (building the checker is not using it)."""
     src = os.path.join(_HERE, "cco_oracle.c")
@@ -76,6 +85,8 @@ def lib():
         L.orc_train.argtypes = [C.c_int, C.POINTER(_Csr), C.POINTER(_Params), C.c_int32, C.c_int, C.c_int,
                                 C.POINTER(_Result)]
         L.orc_free_result.argtypes = [C.POINTER(_Result)]
+        L.orc_ingest.argtypes = [C.c_int, C.POINTER(_Events), C.c_int64, C.c_int32, C.POINTER(C.c_int32), C.POINTER(_Ingested)]
+        L.orc_free_ingested.argtypes = [C.POINTER(_Ingested)]
         _lib = L
     return _lib
 
@@ -250,6 +261,32 @@ def train(mats: list[Csr], params: list[Params], seed: int, flags: int = 0, n_th
                              int(r.products), int(r.distinct_cells), int(r.nnz_a), int(r.nnz_b)))
         L.orc_free_result(C.byref(r))
     return out
+
+
+def ingest(events, n_users_raw: int, min_events_per_user: int = 0):
+    """Preparator.prepare on integer-tokenised events.  events = [(users int64[], items int32[], n_items_raw)],
+    type 0 = primary.  -> (user_map int32[n_users_raw], [(Csr, item_map int32[n_items_raw])])."""
+    L = lib()
+    n = len(events)
+    keep = []
+    ev = (_Events * n)()
+    for t, (u, i, ni) in enumerate(events):
+        u = np.ascontiguousarray(u, dtype=np.int64)
+        i = np.ascontiguousarray(i, dtype=np.int32)
+        keep.append((u, i))
+        ev[t] = _Events(len(u), u.ctypes.data_as(C.POINTER(C.c_int64)), i.ctypes.data_as(C.POINTER(C.c_int32)), ni)
+    user_map = np.zeros(max(n_users_raw, 1), dtype=np.int32)
+    out = (_Ingested * n)()
+    if L.orc_ingest(n, ev, n_users_raw, min_events_per_user, user_map.ctypes.data_as(C.POINTER(C.c_int32)), out):
+        raise OracleError(L.orc_last_error().decode())
+    res = []
+    for t, o in enumerate(out):
+        rp = _take(o.row_ptr, o.n_rows + 1, np.int64)
+        ci = _take(o.col_idx, int(rp[-1]), np.int32)
+        im = _take(o.item_map, events[t][2], np.int32)
+        res.append((Csr(int(o.n_rows), int(o.n_cols), rp, ci), im))
+        L.orc_free_ingested(C.byref(o))
+    return user_map[:n_users_raw], res
 
 
 def cooccurrences_idss(mats: list[Csr], seed: int, max_interesting: int = 50, max_interactions: int = 500,

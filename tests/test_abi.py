@@ -57,3 +57,16 @@ def test_product_package_never_imports_the_oracle():
                 assert "oracle" not in txt.lower() or f in ("cco_kernels.cuh",), f"{f} mentions the oracle"
     k = open(os.path.join(pkg, "csrc", "cco_kernels.cuh")).read()
     assert "#include" not in "".join(l for l in k.splitlines() if "oracle" in l.lower())
+
+
+def test_plain_c_program_links_against_the_abi(tmp_path):
+    """gcc (not nvcc, not g++) compiles a C consumer of the header and links the shared library."""
+    import subprocess
+    from universal_recommender_b200 import _native
+    exe = tmp_path / "c_abi_check"
+    libdir = os.path.dirname(_native.LIB_PATH)
+    subprocess.run(["/usr/bin/gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "abi", "c_abi_check.c"), "-o", str(exe), "-L", libdir, "-lcco_b200",
+                    f"-Wl,-rpath,{libdir}"], check=True)
+    p = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert p.returncode == 0, (p.returncode, p.stdout, p.stderr)

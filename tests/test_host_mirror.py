@@ -88,3 +88,30 @@ def test_seed_to_int_wraps_like_scala():
 def test_engine_json_params():
     ap = ur.URAlgorithmParams.from_engine_json({"indicators": [{"name": "purchase"}, {"name": "view", "maxCorrelatorsPerItem": 50}], "seed": 3})
     assert ap.indicators[1].maxCorrelatorsPerItem == 50 and ap.indicators[0].maxItemsPerUser is None and ap.seed == 3
+
+
+def test_preparator_matches_bruteforce_semantics():
+    """Randomised: shared user dictionary, secondary events of unknown users dropped, duplicates collapse, minEventsPerUser
+    counts duplicate primary events (Preparator.scala:44-87, 102-214)."""
+    import random
+    rng = random.Random(2)
+    for _ in range(50):
+        users = [f"u{i}" for i in range(rng.randrange(1, 12))]
+        items = [f"i{i}" for i in range(rng.randrange(1, 9))]
+        ev = {n: [(rng.choice(users + ["ghost"]), rng.choice(items)) for _ in range(rng.randrange(0, 40))] for n in ("buy", "view")}
+        if not ev["buy"]:
+            continue
+        min_ev = rng.choice([None, 2, 3])
+        prepared = preparator.prepare([("buy", ev["buy"]), ("view", ev["view"])], min_ev)
+        counts = {}
+        for u, _ in ev["buy"]:
+            counts[u] = counts.get(u, 0) + 1
+        keep = {u for u, c in counts.items() if min_ev is None or c >= min_ev}
+        a, b = prepared[0][1], prepared[1][1]
+        assert set(a.row_ids.inverse) == keep and b.row_ids is a.row_ids
+        for name, d in prepared:
+            want = {(u, i) for u, i in ev[name] if u in keep}
+            got = {(d.row_ids.inverse[r], d.column_ids.inverse[c]) for r in range(d.n_rows)
+                   for c in d.col_idx[d.row_ptr[r]:d.row_ptr[r + 1]]}
+            assert got == want
+            assert set(d.column_ids.inverse) == {i for _, i in want}      # item ids come from surviving events only

@@ -568,7 +568,9 @@ __global__ void __launch_bounds__(GROUP == 32 ? 256 : GROUP) k_rows(const RowArg
       const uint32_t dbound = w < (uint32_t)a.n_cols_b ? w : (uint32_t)a.n_cols_b;
       n_pass = (dbound + (uint32_t)a.cap - 1u) / (uint32_t)a.cap;
       if (n_pass == 0) n_pass = 1;
-      tsize = n_pass > 1 ? (uint32_t)a.slots : min((uint32_t)a.slots, max((dbound * (uint32_t)a.tsize_x16) >> 4, 64u));
+      tsize = n_pass > 1 ? (uint32_t)a.slots
+                         : (uint32_t)min((unsigned long long)a.slots,
+                                         max(((unsigned long long)dbound * (unsigned long long)a.tsize_x16) >> 4, 64ull));
       tsize = min((uint32_t)a.slots, (tsize + 32u * NW - 1u) / (32u * NW) * (32u * NW));
     }
     group_sync<GROUP>();  // previous row fully done with shared memory

@@ -5,7 +5,6 @@ the hand-written sm_100a path in csrc/ -- there is no CPU implementation in this
 from __future__ import annotations
 
 import ctypes as C
-import os
 from dataclasses import dataclass
 from typing import Optional, Sequence
 
@@ -237,9 +236,10 @@ _default_ctx: CcoContext | None = None
 
 
 def default_context() -> CcoContext:
+    """Process-wide single-GPU context on device 0 (multi-GPU jobs build theirs with distributed.context_from_env)."""
     global _default_ctx
     if _default_ctx is None:
-        _default_ctx = CcoContext(device=int(os.environ.get("LOCAL_RANK", "0")) if os.environ.get("CCO_USE_LOCAL_RANK") else 0)
+        _default_ctx = CcoContext(device=0)
     return _default_ctx
 
 
