@@ -932,6 +932,48 @@ __global__ void k_partition_rows(const long long *__restrict__ work_prefix, int3
   bounds[r] = lo;
 }
 
+// ---- ingest (Preparator.prepare on integer-tokenised events) ---------------------------------------
+// per-user event counts of the primary type (duplicates count: Preparator.scala:129-132)
+__global__ void k_ingest_count_users(long long n, const long long *__restrict__ user, int32_t *__restrict__ counts) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    atomicAdd(&counts[user[i]], 1);
+}
+// flag[u] = 1 iff user u stays in the dictionary
+__global__ void k_ingest_user_flags(long long n_users_raw, const int32_t *__restrict__ counts, int32_t need,
+                                    uint32_t *__restrict__ flag) {
+  for (long long u = blockIdx.x * (long long)blockDim.x + threadIdx.x; u < n_users_raw; u += (long long)gridDim.x * blockDim.x)
+    flag[u] = counts[u] >= need ? 1u : 0u;
+}
+// map[i] = flag[i] ? pos[i] : -1
+__global__ void k_ingest_make_map(long long n, const uint32_t *__restrict__ flag, const uint32_t *__restrict__ pos,
+                                  int32_t *__restrict__ map) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    map[i] = flag[i] ? (int32_t)pos[i] : -1;
+}
+// items that still have an event of a surviving user (Preparator.scala:184)
+__global__ void k_ingest_item_flags(long long n, const long long *__restrict__ user, const int32_t *__restrict__ item,
+                                    const int32_t *__restrict__ user_map, uint32_t *__restrict__ item_flag) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    if (user_map[user[i]] >= 0) item_flag[item[i]] = 1u;
+}
+// key = (new user << 32 | new item) for surviving events, ~0 for dropped ones (they sort to the end)
+__global__ void k_ingest_keys(long long n, const long long *__restrict__ user, const int32_t *__restrict__ item,
+                              const int32_t *__restrict__ user_map, const int32_t *__restrict__ item_map,
+                              unsigned long long *__restrict__ keys, unsigned long long *__restrict__ n_kept) {
+  unsigned long long kept = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int32_t r = user_map[user[i]];
+    if (r >= 0) {
+      keys[i] = ((unsigned long long)(uint32_t)r << 32) | (uint32_t)item_map[item[i]];
+      ++kept;
+    } else {
+      keys[i] = ~0ULL;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) kept += __shfl_xor_sync(0xffffffffu, kept, o);
+  if ((threadIdx.x & 31) == 0 && kept) atomicAdd(n_kept, kept);
+}
+
 __global__ void k_max_i32(long long n, const int32_t *__restrict__ x, int32_t *__restrict__ out) {
   int32_t m = 0;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
