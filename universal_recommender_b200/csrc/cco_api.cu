@@ -552,13 +552,12 @@ static int run_indicator(cco_ctx *c, Arena &ar, const uint32_t *at_ptr, const in
     h_thr[b] = lim;
     if (b > 0) h_thr[b] = std::min(h_thr[b], h_thr[b - 1]);
   }
-  uint32_t *d_thr;
   int32_t *d_bounds;
-  CKR(ar.alloc(&d_thr, kBins));
   CKR(ar.alloc(&d_bounds, kBins + 3));
-  CK(cudaMemcpyAsync(d_thr, h_thr.data(), sizeof(uint32_t) * kBins, cudaMemcpyHostToDevice, s));
-  CK(cudaStreamSynchronize(s));  // h_thr is a local vector
-  k_bin_bounds<<<1, 32, 0, s>>>(n_my, sorted_work, kBins, d_thr, d_bounds);
+  BinThresholds bt;
+  memset(&bt, 0, sizeof bt);
+  for (int b = 0; b < kBins; ++b) bt.t[b] = h_thr[b];
+  k_bin_bounds<<<1, 32, 0, s>>>(n_my, sorted_work, kBins, bt, d_bounds);
   c->launches++;
   // per-column constants of B' for the fused LLR
   ColTerm *col_terms;

@@ -315,13 +315,16 @@ __global__ void k_row_work(int32_t n_items, const uint32_t *__restrict__ at_ptr,
 
 // bin boundaries inside the work-descending row list: bin b holds rows whose distinct-cell bound
 // D = min(w, n_cols_b) satisfies thresholds[b-1] >= D > thresholds[b]  (thresholds descending)
+struct BinThresholds {
+  uint32_t t[12];  // by value in the launch parameters: no host->device copy, no host sync
+};
 __global__ void k_bin_bounds(int32_t n_rows, const uint32_t *__restrict__ sorted_work, int32_t n_bins,
-                             const uint32_t *__restrict__ thresholds, int32_t *__restrict__ bounds) {
+                             const BinThresholds thresholds, int32_t *__restrict__ bounds) {
   int b = threadIdx.x;
   if (b > n_bins) return;
   if (b == 0) { bounds[0] = 0; return; }
   // first index whose work <= thresholds[b-1]  (sorted descending)
-  uint32_t t = thresholds[b - 1];
+  uint32_t t = thresholds.t[b - 1];
   int lo = 0, hi = n_rows;
   while (lo < hi) {
     int mid = (lo + hi) >> 1;
