@@ -869,15 +869,21 @@ static int train_dataset(cco_ctx *c, const cco_dataset *ds, const cco_indicator_
     total_cols += raw[i].n_cols;
   }
   col_off[n_mats] = total_cols;
+  constexpr int kHistCopies = 16;
+  const long long copy_stride = std::max<long long>(total_cols, 1);
   int32_t *raw_counts;
-  CKR(ar.alloc(&raw_counts, std::max<long long>(total_cols, 1)));
-  CK(cudaMemsetAsync(raw_counts, 0, sizeof(int32_t) * (size_t)std::max<long long>(total_cols, 1), s));
+  CKR(ar.alloc(&raw_counts, (size_t)copy_stride * kHistCopies));
+  CK(cudaMemsetAsync(raw_counts, 0, sizeof(int32_t) * (size_t)copy_stride * kHistCopies, s));
   const long long u_lo = n_users * c->rank / c->world, u_hi = n_users * (c->rank + 1) / c->world;
   for (int i = 0; i < n_mats; ++i) {
     CK(cudaStreamWaitEvent(s, ds->ready[i], 0));  // matrix i has landed (async upload: later ones may still be in flight)
     if (raw[i].nnz == 0 || u_hi == u_lo) continue;
     k_col_histogram<<<grid_for(raw[i].nnz / c->world + 1, 256, c->sm_count), 256, 0, s>>>(u_lo, u_hi, raw[i].rp, raw[i].col,
-                                                                                       raw_counts + col_off[i]);
+                                                                                       raw_counts + col_off[i], kHistCopies, copy_stride);
+    c->launches++;
+  }
+  if (total_cols > 0) {
+    k_sum_copies<<<grid_for(total_cols, 256, c->sm_count), 256, 0, s>>>(total_cols, kHistCopies, copy_stride, raw_counts);
     c->launches++;
   }
   if (c->world > 1) {
@@ -1443,7 +1449,7 @@ int cco_debug_downsample(cco_ctx_t *c, const cco_csr_t *m, int32_t max_interacti
   CKR(ar.alloc(&counts, std::max<int32_t>(m->n_cols, 1)));
   CK(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)std::max<int32_t>(m->n_cols, 1), c->stream));
   if (raw[0].nnz > 0 && m->n_rows > 0)
-    k_col_histogram<<<grid_for(raw[0].nnz, 256, c->sm_count), 256, 0, c->stream>>>(0, m->n_rows, raw[0].rp, raw[0].col, counts);
+    k_col_histogram<<<grid_for(raw[0].nnz, 256, c->sm_count), 256, 0, c->stream>>>(0, m->n_rows, raw[0].rp, raw[0].col, counts, 1, 0);
   DevMat dm;
   CKR(downsample_device(c, ar, raw[0], counts, max_interactions, seed, flags, &dm));
   std::vector<uint32_t> rp32((size_t)m->n_rows + 1);
@@ -1491,7 +1497,7 @@ int cco_debug_cooccurrence(cco_ctx_t *c, const cco_csr_t *a, const cco_csr_t *b,
     CKR(ar.alloc(&counts, std::max<int32_t>(raw[i].n_cols, 1)));
     CK(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)std::max<int32_t>(raw[i].n_cols, 1), s));
     if (raw[i].nnz > 0 && raw[i].n_rows > 0)
-      k_col_histogram<<<grid_for(raw[i].nnz, 256, c->sm_count), 256, 0, s>>>(0, raw[i].n_rows, raw[i].rp, raw[i].col, counts);
+      k_col_histogram<<<grid_for(raw[i].nnz, 256, c->sm_count), 256, 0, s>>>(0, raw[i].n_rows, raw[i].rp, raw[i].col, counts, 1, 0);
     CKR(downsample_device(c, ar, raw[i], counts, 0x7fffffff, 0, 0, &dm[i]));
   }
   const int32_t n_items_a = dm[0].n_cols;
