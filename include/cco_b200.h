@@ -175,6 +175,27 @@ int cco_dataset_free(cco_dataset_t *ds);
  */
 int cco_partition_rows(const int64_t *work_prefix, int32_t n_items, int32_t world_size, int32_t *bounds);
 
+/*
+ * Next row, the ingest right before the boundary: Preparator.prepare + IndexedDatasetSpark.apply
+ * (src/main/scala/Preparator.scala:44-87, 100-216) on integer-tokenised events.  Type 0 is the primary event: the
+ * user dictionary = users with at least min_events_per_user primary events (duplicates counted, :129-132; 0/1 = any
+ * primary event); every type is restricted to those users (:175-178); each type's item dictionary holds the items that
+ * still have an event (:184); duplicates collapse (:201-208).  Dictionaries are in ascending raw-id order.
+ * user_map [n_users_raw] and item_maps[t] [n_items_raw of t] are host arrays filled with the new id or -1.
+ * The resulting dataset is resident in HBM and goes straight into cco_train_dataset.
+ */
+typedef struct {
+  int64_t n_events;
+  const int64_t *user; /* raw user id in [0, n_users_raw) */
+  const int32_t *item; /* raw item id in [0, n_items_raw) */
+  int32_t n_items_raw;
+} cco_events_t;
+int cco_ingest(cco_ctx_t *ctx, int32_t n_types, const cco_events_t *events, int64_t n_users_raw, int32_t min_events_per_user,
+               int32_t *user_map, int32_t *const *item_maps, cco_dataset_t **out);
+int cco_dataset_shape(const cco_dataset_t *ds, int32_t i, int64_t *n_rows, int32_t *n_cols, int64_t *nnz);
+/* test helper: copy matrix i of a resident dataset back to the host (malloc'ed; free with cco_free) */
+int cco_dataset_download(const cco_dataset_t *ds, int32_t i, int64_t **row_ptr, int32_t **col_idx);
+
 /* CUDA-event stopwatch on the context's launch stream (what bench.py brackets its timed region with) */
 int cco_timer_start(cco_ctx_t *ctx);
 int cco_timer_stop(cco_ctx_t *ctx, float *ms);

@@ -442,7 +442,7 @@ static BinCfg make_cfg(cco_ctx *c, int group, int want_slots, int top_k, int n_c
   if (group == 32 && top_k + 32 <= 96) f.cbuf = 128;  // small top_k: a 128-entry buffer doubles the warps per SM (-4 % at C3)
   f.keep_max = std::max(f.final_max, (f.cbuf - group) / 2);
   f.caux = group == 32 ? 0 : f.keep_max;
-  size_t fixed = (size_t)(f.cbuf + f.caux) * 16 + 2 * 256 + 512 + 1024 + (size_t)(group / 32) * 256;  // candidates, x12/x11 tables, ctrl, histogram, queues
+  size_t fixed = (size_t)(f.cbuf + f.caux) * 16 + 2 * 256 + 512 + 1024 + (size_t)(group / 32) * 256 + 2048;  // candidates, x12/x11 tables, ctrl, histogram, queues, level-1 cut histogram
   size_t avail = (c->smem_optin - 1024) / groups;  // slack for static shared memory
   int max_slots = (int)((avail - fixed) / 4) & ~1023;
   f.slots = std::min(want_slots, max_slots);
@@ -552,13 +552,12 @@ static int run_indicator(cco_ctx *c, Arena &ar, const uint32_t *at_ptr, const in
     h_thr[b] = lim;
     if (b > 0) h_thr[b] = std::min(h_thr[b], h_thr[b - 1]);
   }
-  uint32_t *d_thr;
   int32_t *d_bounds;
-  CKR(ar.alloc(&d_thr, kBins));
   CKR(ar.alloc(&d_bounds, kBins + 3));
-  CK(cudaMemcpyAsync(d_thr, h_thr.data(), sizeof(uint32_t) * kBins, cudaMemcpyHostToDevice, s));
-  CK(cudaStreamSynchronize(s));  // h_thr is a local vector
-  k_bin_bounds<<<1, 32, 0, s>>>(n_my, sorted_work, kBins, d_thr, d_bounds);
+  BinThresholds bt;
+  memset(&bt, 0, sizeof bt);
+  for (int b = 0; b < kBins; ++b) bt.t[b] = h_thr[b];
+  k_bin_bounds<<<1, 32, 0, s>>>(n_my, sorted_work, kBins, bt, d_bounds);
   c->launches++;
   // per-column constants of B' for the fused LLR
   ColTerm *col_terms;
@@ -870,15 +869,21 @@ static int train_dataset(cco_ctx *c, const cco_dataset *ds, const cco_indicator_
     total_cols += raw[i].n_cols;
   }
   col_off[n_mats] = total_cols;
+  constexpr int kHistCopies = 16;
+  const long long copy_stride = std::max<long long>(total_cols, 1);
   int32_t *raw_counts;
-  CKR(ar.alloc(&raw_counts, std::max<long long>(total_cols, 1)));
-  CK(cudaMemsetAsync(raw_counts, 0, sizeof(int32_t) * (size_t)std::max<long long>(total_cols, 1), s));
+  CKR(ar.alloc(&raw_counts, (size_t)copy_stride * kHistCopies));
+  CK(cudaMemsetAsync(raw_counts, 0, sizeof(int32_t) * (size_t)copy_stride * kHistCopies, s));
   const long long u_lo = n_users * c->rank / c->world, u_hi = n_users * (c->rank + 1) / c->world;
   for (int i = 0; i < n_mats; ++i) {
     CK(cudaStreamWaitEvent(s, ds->ready[i], 0));  // matrix i has landed (async upload: later ones may still be in flight)
     if (raw[i].nnz == 0 || u_hi == u_lo) continue;
     k_col_histogram<<<grid_for(raw[i].nnz / c->world + 1, 256, c->sm_count), 256, 0, s>>>(u_lo, u_hi, raw[i].rp, raw[i].col,
-                                                                                       raw_counts + col_off[i]);
+                                                                                       raw_counts + col_off[i], kHistCopies, copy_stride);
+    c->launches++;
+  }
+  if (total_cols > 0) {
+    k_sum_copies<<<grid_for(total_cols, 256, c->sm_count), 256, 0, s>>>(total_cols, kHistCopies, copy_stride, raw_counts);
     c->launches++;
   }
   if (c->world > 1) {
@@ -1127,6 +1132,183 @@ int cco_cooccurrences_idss(cco_ctx_t *ctx, int32_t n_mats, const cco_csr_t *mats
   return cco_train(ctx, n_mats, mats, p.data(), seed, flags, out);
 }
 
+int cco_dataset_shape(const cco_dataset_t *ds, int32_t i, int64_t *n_rows, int32_t *n_cols, int64_t *nnz) {
+  if (!ds || i < 0 || i >= ds->n_mats) return set_error(CCO_E_INVALID_ARG, "bad dataset/index");
+  if (n_rows) *n_rows = ds->n_users;
+  if (n_cols) *n_cols = (int32_t)ds->n_cols[i];
+  if (nnz) *nnz = ds->nnz[i];
+  return CCO_OK;
+}
+
+int cco_dataset_download(const cco_dataset_t *ds, int32_t i, int64_t **row_ptr, int32_t **col_idx) {
+  if (!ds || !row_ptr || !col_idx || i < 0 || i >= ds->n_mats) return set_error(CCO_E_INVALID_ARG, "bad argument");
+  cco_ctx *c = ds->ctx;
+  CK(cudaSetDevice(c->device));
+  int64_t *rp = (int64_t *)malloc(sizeof(int64_t) * ((size_t)ds->n_users + 1));
+  int32_t *ci = (int32_t *)malloc(sizeof(int32_t) * (size_t)std::max<long long>(ds->nnz[i], 1));
+  if (!rp || !ci) return set_error(CCO_E_OOM, "malloc failed");
+  CK(cudaStreamSynchronize(c->copy_stream));
+  CK(cudaMemcpyAsync(rp, ds->rp[i], sizeof(int64_t) * ((size_t)ds->n_users + 1), cudaMemcpyDeviceToHost, c->stream));
+  if (ds->nnz[i] > 0)
+    CK(cudaMemcpyAsync(ci, ds->col[i], sizeof(int32_t) * (size_t)ds->nnz[i], cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  *row_ptr = rp;
+  *col_idx = ci;
+  return CCO_OK;
+}
+
+// Preparator.prepare on the device: histogram + scans for the dictionaries, one radix sort + unique
+// per event type for the binary CSR.
+int cco_ingest(cco_ctx_t *c, int32_t n_types, const cco_events_t *ev, int64_t n_users_raw, int32_t min_events_per_user,
+               int32_t *user_map, int32_t *const *item_maps, cco_dataset_t **out) {
+  if (!c || !ev || !user_map || !item_maps || !out || n_types < 1) return set_error(CCO_E_INVALID_ARG, "bad argument");
+  if (n_users_raw < 0 || n_users_raw >= 0x7fffffffLL) return set_error(CCO_E_INVALID_ARG, "n_users_raw out of range");
+  for (int t = 0; t < n_types; ++t) {
+    if (ev[t].n_events < 0 || ev[t].n_events >= 0xffffffffLL || ev[t].n_items_raw < 0)
+      return set_error(CCO_E_INVALID_ARG, "type %d: bad event count / item space", t);
+    if (ev[t].n_events > 0 && (!ev[t].user || !ev[t].item)) return set_error(CCO_E_INVALID_ARG, "type %d: null event arrays", t);
+    if (!item_maps[t] && ev[t].n_items_raw > 0) return set_error(CCO_E_INVALID_ARG, "type %d: null item_map", t);
+    // ids are range-checked on the host: they index device arrays
+    for (int64_t i = 0; i < ev[t].n_events; ++i)
+      if (ev[t].user[i] < 0 || ev[t].user[i] >= n_users_raw || ev[t].item[i] < 0 || ev[t].item[i] >= ev[t].n_items_raw)
+        return set_error(CCO_E_INVALID_ARG, "type %d: user or item id out of range at event %lld", t, (long long)i);
+  }
+  *out = nullptr;
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  c->mail_pending.clear();
+  c->mail_used = 0;
+  Arena ar(s);
+  cco_dataset *d = new cco_dataset();
+  d->ctx = c;
+  d->n_mats = n_types;
+  d->rp.assign(n_types, nullptr);
+  d->col.assign(n_types, nullptr);
+  d->n_cols.assign(n_types, 0);
+  d->nnz.assign(n_types, 0);
+  d->ready.assign(n_types, nullptr);
+  struct G {
+    cco_dataset *d;
+    bool ok = false;
+    ~G() {
+      if (!ok) dataset_release(d);
+    }
+  } g{d};
+  const long long nu = std::max<long long>(n_users_raw, 1);
+  // events to the device
+  std::vector<long long *> d_user(n_types, nullptr);
+  std::vector<int32_t *> d_item(n_types, nullptr);
+  for (int t = 0; t < n_types; ++t) {
+    CKR(ar.alloc(&d_user[t], std::max<long long>(ev[t].n_events, 1)));
+    CKR(ar.alloc(&d_item[t], std::max<long long>(ev[t].n_events, 1)));
+    if (ev[t].n_events > 0) {
+      CK(cudaMemcpyAsync(d_user[t], ev[t].user, sizeof(int64_t) * (size_t)ev[t].n_events, cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpyAsync(d_item[t], ev[t].item, sizeof(int32_t) * (size_t)ev[t].n_events, cudaMemcpyHostToDevice, s));
+    }
+  }
+  // user dictionary from the primary events
+  int32_t *cnt, *d_user_map;
+  uint32_t *uflag, *upos;
+  CKR(ar.alloc(&cnt, nu));
+  CKR(ar.alloc(&uflag, nu + 1));
+  CKR(ar.alloc(&upos, nu + 1));
+  CKR(ar.alloc(&d_user_map, nu));
+  CK(cudaMemsetAsync(cnt, 0, sizeof(int32_t) * (size_t)nu, s));
+  CK(cudaMemsetAsync(uflag, 0, sizeof(uint32_t) * ((size_t)nu + 1), s));
+  if (ev[0].n_events > 0)
+    k_ingest_count_users<<<grid_for(ev[0].n_events, 256, c->sm_count), 256, 0, s>>>(ev[0].n_events, d_user[0], cnt);
+  const int32_t need = min_events_per_user > 1 ? min_events_per_user : 1;
+  if (n_users_raw > 0)
+    k_ingest_user_flags<<<grid_for(n_users_raw, 256, c->sm_count), 256, 0, s>>>(n_users_raw, cnt, need, uflag);
+  CKR(exclusive_sum_u32(c, ar, uflag, upos, nu + 1));
+  if (n_users_raw > 0)
+    k_ingest_make_map<<<grid_for(n_users_raw, 256, c->sm_count), 256, 0, s>>>(n_users_raw, uflag, upos, d_user_map);
+  c->launches += 3;
+  uint32_t n_users = 0;
+  CKR(mail_fetch(c, &n_users, upos + n_users_raw, 4));
+  if (n_users_raw > 0)
+    CK(cudaMemcpyAsync(user_map, d_user_map, sizeof(int32_t) * (size_t)n_users_raw, cudaMemcpyDeviceToHost, s));
+  CKR(mail_wait(c));
+  d->n_users = n_users;
+  for (int t = 0; t < n_types; ++t) {
+    const long long ne = ev[t].n_events, ni = std::max<int32_t>(ev[t].n_items_raw, 1);
+    uint32_t *iflag, *ipos;
+    int32_t *d_item_map;
+    CKR(ar.alloc(&iflag, ni + 1));
+    CKR(ar.alloc(&ipos, ni + 1));
+    CKR(ar.alloc(&d_item_map, ni));
+    CK(cudaMemsetAsync(iflag, 0, sizeof(uint32_t) * ((size_t)ni + 1), s));
+    if (ne > 0)
+      k_ingest_item_flags<<<grid_for(ne, 256, c->sm_count), 256, 0, s>>>(ne, d_user[t], d_item[t], d_user_map, iflag);
+    CKR(exclusive_sum_u32(c, ar, iflag, ipos, ni + 1));
+    k_ingest_make_map<<<grid_for(ni, 256, c->sm_count), 256, 0, s>>>(ev[t].n_items_raw, iflag, ipos, d_item_map);
+    uint32_t n_items = 0;
+    CKR(mail_fetch(c, &n_items, ipos + ev[t].n_items_raw, 4));
+    if (ev[t].n_items_raw > 0)
+      CK(cudaMemcpyAsync(item_maps[t], d_item_map, sizeof(int32_t) * (size_t)ev[t].n_items_raw, cudaMemcpyDeviceToHost, s));
+    // sort surviving (user, item) keys, drop duplicates, rebuild row_ptr
+    unsigned long long *k0, *k1, *d_kept;
+    CKR(ar.alloc(&k0, std::max<long long>(ne, 1)));
+    CKR(ar.alloc(&k1, std::max<long long>(ne, 1)));
+    CKR(ar.alloc(&d_kept, 1));
+    CK(cudaMemsetAsync(d_kept, 0, 8, s));
+    if (ne > 0)
+      k_ingest_keys<<<grid_for(ne, 256, c->sm_count), 256, 0, s>>>(ne, d_user[t], d_item[t], d_user_map, d_item_map, k0, d_kept);
+    c->launches += 3;
+    unsigned long long kept = 0;
+    CKR(mail_fetch(c, &kept, d_kept, 8));
+    CKR(mail_wait(c));
+    d->n_cols[t] = n_items;
+    void *p = nullptr;
+    cudaError_t e = cudaMallocAsync(&p, sizeof(int64_t) * ((size_t)n_users + 1), s);
+    if (e != cudaSuccess) return set_error(CCO_E_OOM, "cudaMallocAsync row_ptr: %s", cudaGetErrorString(e));
+    d->rp[t] = (long long *)p;
+    e = cudaMallocAsync(&p, sizeof(int32_t) * (size_t)std::max<unsigned long long>(kept, 4), s);
+    if (e != cudaSuccess) return set_error(CCO_E_OOM, "cudaMallocAsync col_idx: %s", cudaGetErrorString(e));
+    d->col[t] = (int32_t *)p;
+    CK(cudaEventCreateWithFlags(&d->ready[t], cudaEventDisableTiming));
+    long long n_unique = 0;
+    if (kept > 0) {
+      cub::DoubleBuffer<unsigned long long> db(k0, k1);
+      size_t tb = 0;
+      CK(cub::DeviceRadixSort::SortKeys(nullptr, tb, db, (long long)ne, 0, 64, s));
+      void *tmp;
+      CKR(ar.alloc((char **)&tmp, tb));
+      CK(cub::DeviceRadixSort::SortKeys(tmp, tb, db, (long long)ne, 0, 64, s));
+      ar.release(tmp);
+      unsigned long long *sorted = db.Current(), *other = db.Alternate();
+      uint32_t *flag, *pos;
+      CKR(ar.alloc(&flag, kept + 1));
+      CKR(ar.alloc(&pos, kept + 1));
+      CK(cudaMemsetAsync(flag + kept, 0, 4, s));
+      k_unique_flags<<<grid_for((long long)kept, 256, c->sm_count), 256, 0, s>>>((long long)kept, sorted, flag);
+      CKR(exclusive_sum_u32(c, ar, flag, pos, (long long)kept + 1));
+      uint32_t nuq = 0;
+      CKR(mail_fetch(c, &nuq, pos + kept, 4));
+      k_unique_scatter<<<grid_for((long long)kept, 256, c->sm_count), 256, 0, s>>>((long long)kept, sorted, flag, pos, other, d->col[t]);
+      CKR(mail_wait(c));
+      n_unique = nuq;
+      k_rowptr_from_keys<<<grid_for((long long)n_users + 1, 256, c->sm_count), 256, 0, s>>>((long long)n_users, n_unique, other, d->rp[t]);
+      c->launches += 3;
+      ar.release(flag);
+      ar.release(pos);
+    } else {
+      CK(cudaMemsetAsync(d->rp[t], 0, sizeof(int64_t) * ((size_t)n_users + 1), s));
+    }
+    d->nnz[t] = n_unique;
+    CK(cudaEventRecord(d->ready[t], s));
+    ar.release(k0);
+    ar.release(k1);
+    ar.release(iflag);
+    ar.release(ipos);
+  }
+  CK(cudaStreamSynchronize(s));
+  CK(cudaGetLastError());
+  g.ok = true;
+  *out = d;
+  return CCO_OK;
+}
+
 int cco_partition_rows(const int64_t *work_prefix, int32_t n_items, int32_t world_size, int32_t *bounds) {
   if (!work_prefix || !bounds || n_items < 0 || world_size < 1) return set_error(CCO_E_INVALID_ARG, "bad argument");
   // weight of row i = its products + 1 (so rows without work are spread too); contiguous ranges of equal weight
@@ -1267,7 +1449,7 @@ int cco_debug_downsample(cco_ctx_t *c, const cco_csr_t *m, int32_t max_interacti
   CKR(ar.alloc(&counts, std::max<int32_t>(m->n_cols, 1)));
   CK(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)std::max<int32_t>(m->n_cols, 1), c->stream));
   if (raw[0].nnz > 0 && m->n_rows > 0)
-    k_col_histogram<<<grid_for(raw[0].nnz, 256, c->sm_count), 256, 0, c->stream>>>(0, m->n_rows, raw[0].rp, raw[0].col, counts);
+    k_col_histogram<<<grid_for(raw[0].nnz, 256, c->sm_count), 256, 0, c->stream>>>(0, m->n_rows, raw[0].rp, raw[0].col, counts, 1, 0);
   DevMat dm;
   CKR(downsample_device(c, ar, raw[0], counts, max_interactions, seed, flags, &dm));
   std::vector<uint32_t> rp32((size_t)m->n_rows + 1);
@@ -1315,7 +1497,7 @@ int cco_debug_cooccurrence(cco_ctx_t *c, const cco_csr_t *a, const cco_csr_t *b,
     CKR(ar.alloc(&counts, std::max<int32_t>(raw[i].n_cols, 1)));
     CK(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)std::max<int32_t>(raw[i].n_cols, 1), s));
     if (raw[i].nnz > 0 && raw[i].n_rows > 0)
-      k_col_histogram<<<grid_for(raw[i].nnz, 256, c->sm_count), 256, 0, s>>>(0, raw[i].n_rows, raw[i].rp, raw[i].col, counts);
+      k_col_histogram<<<grid_for(raw[i].nnz, 256, c->sm_count), 256, 0, s>>>(0, raw[i].n_rows, raw[i].rp, raw[i].col, counts, 1, 0);
     CKR(downsample_device(c, ar, raw[i], counts, 0x7fffffff, 0, 0, &dm[i]));
   }
   const int32_t n_items_a = dm[0].n_cols;

@@ -165,11 +165,16 @@ __global__ void k_check_rows(long long n_rows, int32_t n_cols, const long long *
 }
 
 // raw column counts c_j of rows [row_begin,row_end) (numNonZeroElementsPerColumn of the raw matrix)
+// The counters are REPLICATED (n_copies arrays, copy_stride apart, chosen by CTA): with Zipf-skewed items 8 % of all
+// entries hit one column, and its atomics serialise in one L2 slice (~0.3 ms per 12.5 M-entry matrix at C3);
+// k_sum_copies folds the copies back into copy 0.
 __global__ void k_col_histogram(long long row_begin, long long row_end, const long long *__restrict__ rp,
-                                const int32_t *__restrict__ col, int32_t *__restrict__ counts) {
+                                const int32_t *__restrict__ col, int32_t *__restrict__ counts, int n_copies,
+                                long long copy_stride) {
   // element-parallel over the contiguous slice rp[row_begin]..rp[row_end]; warp-uniform trip count
   const long long s = rp[row_begin], e = rp[row_end];
   const int lane = threadIdx.x & 31;
+  int32_t *mine = counts + (long long)(blockIdx.x % n_copies) * copy_stride;
   for (long long q0 = s + blockIdx.x * (long long)blockDim.x + (threadIdx.x & ~31); q0 < e;
        q0 += (long long)gridDim.x * blockDim.x) {
     const long long q = q0 + lane;
@@ -179,12 +184,18 @@ __global__ void k_col_histogram(long long row_begin, long long row_end, const lo
       int32_t c = col[q];
       // warp-aggregate lanes hitting the same column (Zipf-hot columns)
       unsigned peers = __match_any_sync(am, c);
-      if ((__ffs(peers) - 1) == lane) atomicAdd(&counts[c], __popc(peers));
+      if ((__ffs(peers) - 1) == lane) atomicAdd(&mine[c], __popc(peers));
     }
   }
 }
+__global__ void k_sum_copies(long long n, int n_copies, long long copy_stride, int32_t *__restrict__ counts) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int32_t acc = counts[i];
+    for (int k = 1; k < n_copies; ++k) acc += counts[i + k * copy_stride];
+    counts[i] = acc;
+  }
+}
 
-// perRowSampleRate of sampleDownAndBinarize (hoisted: once per row)
 // column histogram of the entries [*lo, *hi) of a column-index array (bounds read on the device, 32-bit offsets)
 __global__ void k_col_histogram_u32(const uint32_t *__restrict__ lo, const uint32_t *__restrict__ hi,
                                     const int32_t *__restrict__ col, int32_t *__restrict__ counts) {
@@ -315,13 +326,16 @@ __global__ void k_row_work(int32_t n_items, const uint32_t *__restrict__ at_ptr,
 
 // bin boundaries inside the work-descending row list: bin b holds rows whose distinct-cell bound
 // D = min(w, n_cols_b) satisfies thresholds[b-1] >= D > thresholds[b]  (thresholds descending)
+struct BinThresholds {
+  uint32_t t[12];  // by value in the launch parameters: no host->device copy, no host sync
+};
 __global__ void k_bin_bounds(int32_t n_rows, const uint32_t *__restrict__ sorted_work, int32_t n_bins,
-                             const uint32_t *__restrict__ thresholds, int32_t *__restrict__ bounds) {
+                             const BinThresholds thresholds, int32_t *__restrict__ bounds) {
   int b = threadIdx.x;
   if (b > n_bins) return;
   if (b == 0) { bounds[0] = 0; return; }
   // first index whose work <= thresholds[b-1]  (sorted descending)
-  uint32_t t = thresholds[b - 1];
+  uint32_t t = thresholds.t[b - 1];
   int lo = 0, hi = n_rows;
   while (lo < hi) {
     int mid = (lo + hi) >> 1;
@@ -500,6 +514,7 @@ __device__ int reduce_candidates(uint4 *tk, uint4 *aux, int n, int k, int M, int
   return kept;
 }
 
+constexpr int kCutBins = 1024;  // level-1 integer cut: colB histogram bins (cells with colB >= kCutBins are never cut)
 constexpr int kDomLevels = 15;  // dominance filter keeps cfail[1..15] in ctrl[41..55]
 constexpr int kX12N = 31;  // x12tab[j] = xLogX(ra - j) for j < 31; x12tab[31] = xLogX(N - ra)
 
@@ -542,7 +557,8 @@ __global__ void __launch_bounds__(GROUP == 32 ? 256 : GROUP) k_rows(const RowArg
   int *ctrl = reinterpret_cast<int *>(x11tab + 32);  // [0] ncand [1] have_thr [4..7] threshold entry [16..27] select state [40..55] dominance frontier [64..64+NW) per-warp list sizes
   int *hist = ctrl + 128;                                     // 256 bins of the radix select
   uint32_t *wqueue = reinterpret_cast<uint32_t *>(hist + 256);  // NW * 64 queued cells awaiting evaluation
-  uint32_t *table = wqueue + NW * 64;
+  uint32_t *h1 = wqueue + NW * 64;   // kCutBins/2 words: u16 histogram of colB over the strongly positive k11 == 1 cells
+  uint32_t *table = h1 + kCutBins / 2;
   volatile int *vctrl = ctrl;
 
   const int row_begin = a.bin_bounds[a.bin], row_end = a.bin_bounds[a.bin + 1];
@@ -663,6 +679,56 @@ __global__ void __launch_bounds__(GROUP == 32 ? 256 : GROUP) k_rows(const RowArg
         group_sync<GROUP>();
         continue;
       }
+      // ---- level-1 integer cut (exact) ---------------------------------------------------------------
+      // On the strongly positive side (2*rowA*colB < k11*N) the LLR of k11 == 1 cells is strictly decreasing in colB, so
+      // the smallest colB c1 with >= top_k such cells at or below it bounds the row's k-th best from below: k11 == 1 cells
+      // with colB > c1 can never be kept and are dropped by an integer compare in the filter stage.
+      int cut1 = 0x7fffffff;
+      if (a.row_work[item] < 65536u) {   // u16 bins cannot overflow
+        for (int i = gtid; i < kCutBins / 2; i += GROUP) h1[i] = 0u;
+        group_sync<GROUP>();
+        for (uint32_t q0 = 0; q0 < n_mine; q0 += 32) {
+          const uint32_t q = q0 + lane;
+          if (q < n_mine) {
+            const uint32_t word = table[seg_lo + q];
+            const uint32_t b = word >> cbits;
+            if ((word & cmask) == 1u && !(a.self && (int)b == item)) {
+              const uint32_t cb = (uint32_t)a.marg_b[b];
+              if (cb < (uint32_t)kCutBins && 2ull * (unsigned long long)ra * cb < (unsigned long long)N)
+                atomicAdd(&h1[cb >> 1], 1u << (16u * (cb & 1u)));
+            }
+          }
+        }
+        group_sync<GROUP>();
+        if (gtid < 32) {
+          // lane l owns bins [32 l, 32 l + 32): 16 words
+          uint32_t sum = 0;
+          for (int wi = 0; wi < 16; ++wi) { const uint32_t v = h1[gtid * 16 + wi]; sum += (v & 0xffffu) + (v >> 16); }
+          uint32_t incl = sum;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (gtid >= d) incl += v;
+          }
+          const uint32_t excl = incl - sum;
+          int found = 0x7fffffff;
+          if (excl < (uint32_t)a.top_k && incl >= (uint32_t)a.top_k) {
+            uint32_t run = excl;
+            for (int wi = 0; wi < 16 && found == 0x7fffffff; ++wi) {
+              const uint32_t v = h1[gtid * 16 + wi];
+              run += v & 0xffffu;
+              if (run >= (uint32_t)a.top_k) { found = gtid * 32 + 2 * wi; break; }
+              run += v >> 16;
+              if (run >= (uint32_t)a.top_k) { found = gtid * 32 + 2 * wi + 1; break; }
+            }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) found = min(found, __shfl_xor_sync(0xffffffffu, found, o));
+          if (gtid == 0) ctrl[9] = found;
+        }
+        group_sync<GROUP>();
+        cut1 = vctrl[9];
+      }
       // ---- score + select -----------------------------------------------------------------------------------
       const double x_ra = x12tab[0], x_nra = x12tab[kX12N];
       const double row_e = varargs ? __dsub_rn(xN, __dadd_rn(__dadd_rn(0.0, x_ra), x_nra))
@@ -689,6 +755,8 @@ __global__ void __launch_bounds__(GROUP == 32 ? 256 : GROUP) k_rows(const RowArg
               const long long cb = a.marg_b[b];
               const bool pos_side = (unsigned long long)ra * (unsigned long long)cb < (unsigned long long)k11 * (unsigned long long)N;
               surv = !(pos_side && k11 <= (uint32_t)kDomLevels && (int)cb >= vctrl[40 + k11]);
+              if (k11 == 1u && (int)cb > cut1 && cb < kCutBins && 2ull * (unsigned long long)ra * (unsigned long long)cb < (unsigned long long)N)
+                surv = false;   // beyond the level-1 integer cut
             }
           }
           const unsigned m = __ballot_sync(0xffffffffu, surv);
@@ -876,6 +944,48 @@ __global__ void k_partition_rows(const long long *__restrict__ work_prefix, int3
     if (work_prefix[mid] + mid < target) lo = mid + 1; else hi = mid;
   }
   bounds[r] = lo;
+}
+
+// ---- ingest (Preparator.prepare on integer-tokenised events) ---------------------------------------
+// per-user event counts of the primary type (duplicates count: Preparator.scala:129-132)
+__global__ void k_ingest_count_users(long long n, const long long *__restrict__ user, int32_t *__restrict__ counts) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    atomicAdd(&counts[user[i]], 1);
+}
+// flag[u] = 1 iff user u stays in the dictionary
+__global__ void k_ingest_user_flags(long long n_users_raw, const int32_t *__restrict__ counts, int32_t need,
+                                    uint32_t *__restrict__ flag) {
+  for (long long u = blockIdx.x * (long long)blockDim.x + threadIdx.x; u < n_users_raw; u += (long long)gridDim.x * blockDim.x)
+    flag[u] = counts[u] >= need ? 1u : 0u;
+}
+// map[i] = flag[i] ? pos[i] : -1
+__global__ void k_ingest_make_map(long long n, const uint32_t *__restrict__ flag, const uint32_t *__restrict__ pos,
+                                  int32_t *__restrict__ map) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    map[i] = flag[i] ? (int32_t)pos[i] : -1;
+}
+// items that still have an event of a surviving user (Preparator.scala:184)
+__global__ void k_ingest_item_flags(long long n, const long long *__restrict__ user, const int32_t *__restrict__ item,
+                                    const int32_t *__restrict__ user_map, uint32_t *__restrict__ item_flag) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    if (user_map[user[i]] >= 0) item_flag[item[i]] = 1u;
+}
+// key = (new user << 32 | new item) for surviving events, ~0 for dropped ones (they sort to the end)
+__global__ void k_ingest_keys(long long n, const long long *__restrict__ user, const int32_t *__restrict__ item,
+                              const int32_t *__restrict__ user_map, const int32_t *__restrict__ item_map,
+                              unsigned long long *__restrict__ keys, unsigned long long *__restrict__ n_kept) {
+  unsigned long long kept = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int32_t r = user_map[user[i]];
+    if (r >= 0) {
+      keys[i] = ((unsigned long long)(uint32_t)r << 32) | (uint32_t)item_map[item[i]];
+      ++kept;
+    } else {
+      keys[i] = ~0ULL;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) kept += __shfl_xor_sync(0xffffffffu, kept, o);
+  if ((threadIdx.x & 31) == 0 && kept) atomicAdd(n_kept, kept);
 }
 
 __global__ void k_max_i32(long long n, const int32_t *__restrict__ x, int32_t *__restrict__ out) {

@@ -169,6 +169,37 @@ class CcoContext:
         N.check(self._L.cco_train_dataset(self._h, ds, self._params_array(params), C.c_int32(_to_i32(seed)), flags, C.byref(res)))
         return self._collect(res, n, copy_arrays)
 
+    def ingest(self, events, n_users_raw: int, min_events_per_user: int = 0):
+        """Preparator.prepare on the device.  events = [(users int64[], items int32[], n_items_raw)], type 0
+        = primary.  -> (dataset for train_dataset, user_map int32[n_users_raw], [item_map int32[n_items_raw]])."""
+        n = len(events)
+        keep, ev = [], (N.EventsT * n)()
+        item_maps = [np.zeros(max(ni, 1), dtype=np.int32) for (_, _, ni) in events]
+        for t, (u, i, ni) in enumerate(events):
+            u = np.ascontiguousarray(u, dtype=np.int64)
+            i = np.ascontiguousarray(i, dtype=np.int32)
+            keep.append((u, i))
+            ev[t] = N.EventsT(len(u), u.ctypes.data_as(C.POINTER(C.c_int64)), i.ctypes.data_as(C.POINTER(C.c_int32)), ni)
+        user_map = np.zeros(max(n_users_raw, 1), dtype=np.int32)
+        maps = (C.POINTER(C.c_int32) * n)(*[m.ctypes.data_as(C.POINTER(C.c_int32)) for m in item_maps])
+        ds = C.c_void_p()
+        N.check(self._L.cco_ingest(self._h, n, ev, n_users_raw, min_events_per_user, user_map.ctypes.data_as(C.POINTER(C.c_int32)),
+                                   maps, C.byref(ds)))
+        return (ds, n), user_map[:n_users_raw], [m[:ni] for m, (_, _, ni) in zip(item_maps, events)]
+
+    def dataset_matrix(self, dataset, i: int):
+        """(n_rows, n_cols, row_ptr, col_idx) of matrix i of a resident dataset, copied to the host (tests)."""
+        ds, _ = dataset
+        nr, nc, nnz = C.c_int64(), C.c_int32(), C.c_int64()
+        N.check(self._L.cco_dataset_shape(ds, i, C.byref(nr), C.byref(nc), C.byref(nnz)))
+        prp, pci = C.POINTER(C.c_int64)(), C.POINTER(C.c_int32)()
+        N.check(self._L.cco_dataset_download(ds, i, C.byref(prp), C.byref(pci)))
+        rp = np.ctypeslib.as_array(prp, shape=(nr.value + 1,)).copy()
+        ci = np.ctypeslib.as_array(pci, shape=(nnz.value,)).copy() if nnz.value else np.zeros(0, np.int32)
+        self._L.cco_free(prp)
+        self._L.cco_free(pci)
+        return nr.value, nc.value, rp, ci
+
     def free_dataset(self, dataset):
         self._L.cco_dataset_free(dataset[0])
 
