@@ -93,6 +93,92 @@ static inline double llr_from_marginals(int64_t with_a, int64_t with_b, int64_t 
 }
 
 /* ---------------------------------------------------------------------------------------------
+ * Shared-memory parallel helpers of the CPU arm (OpenMP).  They only change HOW FAST the restated
+ * algorithm runs on the host cores (bench.py --impl reference), never what it computes.
+ * ------------------------------------------------------------------------------------------- */
+static int g_threads = 0; /* set by orc_train / orc_set_threads; 0 = OpenMP default */
+void orc_set_threads(int n) {
+  g_threads = n > 0 ? n : 0;
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n); /* overrides OMP_NUM_THREADS (torchrun exports 1 to its children) */
+#endif
+}
+static int team_size(void) {
+#ifdef _OPENMP
+  return g_threads > 0 ? g_threads : omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+/* counts[j] = number of entries of idx[0..n) equal to j; per-thread private histograms (at most 32 of them, so the
+ * scratch stays <= 32 * n_cols * 4 bytes) folded column-parallel: no atomics on Zipf-hot columns */
+static int col_histogram(const int32_t *idx, int64_t n, int32_t n_cols, int32_t *counts) {
+  const int32_t nc = n_cols > 0 ? n_cols : 1;
+  int T = team_size();
+  if (T > 32) T = 32;
+  if (n < (1 << 16) || T < 2) {
+    memset(counts, 0, sizeof(int32_t) * (size_t)nc);
+    for (int64_t i = 0; i < n; ++i) counts[idx[i]]++;
+    return 0;
+  }
+  int32_t *priv = (int32_t *)calloc((size_t)T * (size_t)nc, sizeof(int32_t));
+  if (!priv) FAIL("out of memory");
+#pragma omp parallel num_threads(T)
+  {
+#ifdef _OPENMP
+    const int t = omp_get_thread_num(), nt = omp_get_num_threads();
+#else
+    const int t = 0, nt = 1;
+#endif
+    int32_t *mine = priv + (size_t)t * (size_t)nc;
+    const int64_t lo = n * t / nt, hi = n * (t + 1) / nt;
+    for (int64_t i = lo; i < hi; ++i) mine[idx[i]]++;
+#pragma omp barrier
+#pragma omp for schedule(static)
+    for (int32_t j = 0; j < nc; ++j) {
+      int32_t acc = 0;
+      for (int k = 0; k < nt; ++k) acc += priv[(size_t)k * (size_t)nc + j];
+      counts[j] = acc;
+    }
+  }
+  free(priv);
+  return 0;
+}
+
+/* in-place inclusive prefix sum of x[1..n] (x[0] stays): two-pass block scan */
+static void prefix_sum_i64(int64_t *x, int64_t n) {
+  int T = team_size();
+  if (n < (1 << 16) || T < 2) {
+    for (int64_t r = 0; r < n; ++r) x[r + 1] += x[r];
+    return;
+  }
+  if (T > 64) T = 64;
+  int64_t block_sum[65];
+  memset(block_sum, 0, sizeof block_sum);
+#pragma omp parallel num_threads(T)
+  {
+#ifdef _OPENMP
+    const int t = omp_get_thread_num(), nt = omp_get_num_threads();
+#else
+    const int t = 0, nt = 1;
+#endif
+    const int64_t lo = n * t / nt, hi = n * (t + 1) / nt;
+    int64_t s = 0;
+    for (int64_t r = lo; r < hi; ++r) s += x[r + 1];
+    block_sum[t + 1] = s;
+#pragma omp barrier
+#pragma omp single
+    for (int k = 0; k < nt; ++k) block_sum[k + 1] += block_sum[k];
+    int64_t run = x[0] + block_sum[t];
+    for (int64_t r = lo; r < hi; ++r) {
+      run += x[r + 1];
+      x[r + 1] = run;
+    }
+  }
+}
+
+/* ---------------------------------------------------------------------------------------------
  * Deterministic counter-based sampler (this repo's definition, shared bit-for-bit with the CUDA
  * path -- include/cco_b200.h "Sampler").  Mahout seeds java.util.Random per Spark block
  * (MurmurHash(keys(0), seed)) and draws one nextDouble() per non-zero in hash-iteration order,
@@ -215,9 +301,8 @@ int orc_downsample(const orc_csr_t *in, int32_t m, int32_t seed, int flags, int6
   int64_t *rp = (int64_t *)malloc(sizeof(int64_t) * (size_t)(in->n_rows + 1));
   int32_t *ci = (int32_t *)malloc(sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1));
   if (!cc || !rp || !ci) FAIL("out of memory");
-  for (int64_t i = 0; i < nnz; ++i) cc[in->col_idx[i]]++;
+  if (col_histogram(in->col_idx, nnz, in->n_cols, cc)) return -1;
   if (raw_col_counts) memcpy(raw_col_counts, cc, sizeof(int32_t) * (size_t)in->n_cols);
-  if (new_col_counts) memset(new_col_counts, 0, sizeof(int32_t) * (size_t)in->n_cols);
   /* pass 1 (parallel over rows): kept entries per row; the keep decision is a pure function of (seed, row, col) */
   rp[0] = 0;
 #pragma omp parallel for schedule(static, 4096)
@@ -231,7 +316,7 @@ int orc_downsample(const orc_csr_t *in, int32_t m, int32_t seed, int flags, int6
     for (int64_t i = s; i < e; ++i) kept += keep_entry(in, cc, r, d, row_rate, i, m, seed);
     rp[r + 1] = kept;
   }
-  for (int64_t r = 0; r < in->n_rows; ++r) rp[r + 1] += rp[r];
+  prefix_sum_i64(rp, in->n_rows);
   /* pass 2 (parallel over rows): ordered write */
 #pragma omp parallel for schedule(static, 4096)
   for (int64_t r = 0; r < in->n_rows; ++r) {
@@ -244,28 +329,37 @@ int orc_downsample(const orc_csr_t *in, int32_t m, int32_t seed, int flags, int6
     for (int64_t i = s; i < e; ++i)
       if (keep_entry(in, cc, r, d, row_rate, i, m, seed)) ci[w++] = in->col_idx[i];
   }
-  if (new_col_counts) {
-    int64_t total = rp[in->n_rows];
-    for (int64_t i = 0; i < total; ++i) new_col_counts[ci[i]]++;
-  }
+  if (new_col_counts && col_histogram(ci, rp[in->n_rows], in->n_cols, new_col_counts)) return -1;
   free(cc);
   *row_ptr = rp;
   *col_idx = ci;
   return 0;
 }
 
-/* item-major view of a canonical CSR: users of each item, ascending (what `drmA.t` provides) */
+/* item-major view of a canonical CSR: users of each item (what `drmA.t` provides).  The scatter runs on every host
+ * thread with an atomic per-item cursor, so the order of users inside an item is arbitrary -- the integer
+ * co-occurrence counts do not depend on it. */
 static int transpose(const int64_t *rp, const int32_t *ci, int64_t n_rows, int32_t n_cols,
                      int64_t **t_ptr, int32_t **t_idx) {
   int64_t nnz = rp[n_rows];
   int64_t *tp = (int64_t *)calloc((size_t)n_cols + 2, sizeof(int64_t));
   int32_t *ti = (int32_t *)malloc(sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1));
-  if (!tp || !ti) FAIL("out of memory");
-  for (int64_t i = 0; i < nnz; ++i) tp[ci[i] + 2]++;
-  for (int32_t j = 0; j < n_cols; ++j) tp[j + 2] += tp[j + 1];
+  int32_t *cnt = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n_cols > 0 ? n_cols : 1));
+  int64_t *cur = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n_cols > 0 ? n_cols : 1));
+  if (!tp || !ti || !cnt || !cur) FAIL("out of memory");
+  if (col_histogram(ci, nnz, n_cols, cnt)) return -1;
+  for (int32_t j = 0; j < n_cols; ++j) tp[j + 1] = cnt[j];
+  prefix_sum_i64(tp, n_cols);
+  memcpy(cur, tp, sizeof(int64_t) * (size_t)n_cols);
+#pragma omp parallel for schedule(static, 4096)
   for (int64_t r = 0; r < n_rows; ++r)
-    for (int64_t i = rp[r]; i < rp[r + 1]; ++i) ti[tp[ci[i] + 1]++] = (int32_t)r;
-  *t_ptr = tp; /* tp[j]..tp[j+1] now delimits item j */
+    for (int64_t i = rp[r]; i < rp[r + 1]; ++i) {
+      int64_t pos = __atomic_fetch_add(&cur[ci[i]], 1, __ATOMIC_RELAXED);
+      ti[pos] = (int32_t)r;
+    }
+  free(cnt);
+  free(cur);
+  *t_ptr = tp; /* tp[j]..tp[j+1] delimits item j */
   *t_idx = ti;
   return 0;
 }
@@ -438,23 +532,24 @@ static int similarity(const int64_t *at_ptr, const int32_t *at_idx, int32_t n_it
   out->n_rows = n_items_a;
   out->n_cols = n_items_b;
   out->row_ptr = (int64_t *)malloc(sizeof(int64_t) * ((size_t)n_items_a + 1));
-  int64_t total = 0;
-  for (int32_t i = 0; i < n_items_a; ++i) total += len[i];
+  if (!out->row_ptr) FAIL("out of memory");
+  out->row_ptr[0] = 0;
+  for (int32_t i = 0; i < n_items_a; ++i) out->row_ptr[i + 1] = len[i];
+  prefix_sum_i64(out->row_ptr, n_items_a);
+  const int64_t total = out->row_ptr[n_items_a];
   out->col_idx = (int32_t *)malloc(sizeof(int32_t) * (size_t)(total > 0 ? total : 1));
   out->llr = (double *)malloc(sizeof(double) * (size_t)(total > 0 ? total : 1));
   out->count = (int32_t *)malloc(sizeof(int32_t) * (size_t)(total > 0 ? total : 1));
-  if (!out->row_ptr || !out->col_idx || !out->llr || !out->count) FAIL("out of memory");
-  int64_t w = 0;
-  out->row_ptr[0] = 0;
+  if (!out->col_idx || !out->llr || !out->count) FAIL("out of memory");
+#pragma omp parallel for schedule(static, 1024)
   for (int32_t i = 0; i < n_items_a; ++i) {
-    for (int32_t t = 0; t < len[i]; ++t) {
+    int64_t w = out->row_ptr[i];
+    for (int32_t t = 0; t < len[i]; ++t, ++w) {
       const cand_t *c = &kept[(size_t)i * stride + t];
       out->col_idx[w] = c->col;
       out->llr[w] = c->llr;
       out->count[w] = c->cnt;
-      ++w;
     }
-    out->row_ptr[i + 1] = w;
   }
   out->products = products;
   out->distinct_cells = distinct;
@@ -474,6 +569,7 @@ static int similarity(const int64_t *at_ptr, const int32_t *at_idx, int32_t n_it
 int orc_train(int n_mats, const orc_csr_t *mats, const orc_params_t *params, int32_t seed, int flags,
               int n_threads, orc_result_t *results) {
   if (n_mats < 1) FAIL("need at least the primary matrix");
+  orc_set_threads(n_threads); /* every parallel region of this call, not only the similarity loop */
   memset(results, 0, sizeof(orc_result_t) * (size_t)n_mats);
   for (int i = 0; i < n_mats; ++i) {
     if (validate(&mats[i])) return -1;

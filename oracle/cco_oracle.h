@@ -118,6 +118,9 @@ void orc_free_ingested(orc_ingested_t *r);
 void orc_free_result(orc_result_t *r);
 void orc_free(void *p);
 int orc_max_threads(void);
+/* thread count of every OpenMP region of later calls on this thread (0 = OpenMP default); orc_train calls it with its
+ * n_threads argument, so OMP_NUM_THREADS=1 exported by a launcher (torchrun) does not serialise the CPU arm */
+void orc_set_threads(int n);
 const char *orc_last_error(void);
 
 #ifdef __cplusplus

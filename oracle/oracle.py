@@ -74,6 +74,8 @@ def lib():
         L.orc_u01.argtypes = [C.c_uint64]
         L.orc_last_error.restype = C.c_char_p
         L.orc_max_threads.restype = C.c_int
+        L.orc_set_threads.argtypes = [C.c_int]
+        L.orc_set_threads.restype = None
         L.orc_free.argtypes = [C.c_void_p]
         L.orc_canonicalize.argtypes = [C.POINTER(_Csr), C.POINTER(C.POINTER(C.c_int64)),
                                        C.POINTER(C.POINTER(C.c_int32))]
@@ -261,6 +263,27 @@ def train(mats: list[Csr], params: list[Params], seed: int, flags: int = 0, n_th
                              int(r.products), int(r.distinct_cells), int(r.nnz_a), int(r.nnz_b)))
         L.orc_free_result(C.byref(r))
     return out
+
+
+def time_train(mats: list[Csr], params: list[Params], seed: int, flags: int = 0, n_threads: int = 0):
+    """The CPU arm's timed call: orc_train only (no numpy copies of the result) -> (seconds, threads used, stats of the
+    run: products / distinct cells / kept cells per indicator)."""
+    import time
+    L = lib()
+    n = len(mats)
+    cm = (_Csr * n)(*[m._c() for m in mats])
+    cp = (_Params * n)(*[_Params(p.max_interactions, p.top_k, 0 if p.min_llr is None else 1,
+                                 0.0 if p.min_llr is None else float(p.min_llr)) for p in params])
+    res = (_Result * n)()
+    t0 = time.perf_counter()
+    rc = L.orc_train(n, cm, cp, seed, flags, n_threads, res)
+    dt = time.perf_counter() - t0
+    if rc:
+        raise OracleError(L.orc_last_error().decode())
+    stats = [(int(r.products), int(r.distinct_cells), int(r.row_ptr[r.n_rows])) for r in res]
+    for r in res:
+        L.orc_free_result(C.byref(r))
+    return dt, (n_threads if n_threads > 0 else L.orc_max_threads()), stats
 
 
 def ingest(events, n_users_raw: int, min_events_per_user: int = 0):

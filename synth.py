@@ -7,6 +7,7 @@ The matrices come out exactly as Preparator would build them: binary, deduplicat
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -81,10 +82,30 @@ def to_binary_csr(users: np.ndarray, items: np.ndarray, n_users: int, n_items: i
     return rp, c
 
 
+def _cache_path(name: str, cfg: dict):
+    """Generated matrices are cached (np.savez, /dev/shm by default) so that the processes of one GPU lease -- tests,
+    the reference arm, the bench -- generate a workload once.  CCO_SYNTH_CACHE=0 disables, any other value = directory."""
+    d = os.environ.get("CCO_SYNTH_CACHE", "/dev/shm/cco_synth")
+    if d == "0" or cfg["n_events"] < 2_000_000:
+        return None
+    key = "_".join(f"{k}{cfg[k]}" for k in sorted(cfg))
+    return os.path.join(d, f"{name}_{key}.npz")
+
+
 def make(name: str, **override) -> Workload:
     cfg = dict(CONFIGS[name])
     cfg.update(override)
     w = Workload(name=name, **cfg)
+    cp = _cache_path(name, cfg)
+    if cp and os.path.exists(cp):
+        try:
+            z = np.load(cp)
+            w.n_users = int(z["n_users"])
+            w.mats = [(w.n_users, w.n_items, z[f"rp{t}"], z[f"ci{t}"]) for t in range(w.n_types)]
+            w.events_per_type = [w.n_events // w.n_types] * w.n_types
+            return w
+        except Exception:
+            pass
     per_type = w.n_events // w.n_types
     w.mats, w.events_per_type = [], []
     keep_users = None
@@ -104,4 +125,13 @@ def make(name: str, **override) -> Workload:
         rp, ci = to_binary_csr(users, items, w.n_users, w.n_items)
         w.mats.append((w.n_users, w.n_items, rp, ci))
         w.events_per_type.append(per_type)
+    if cp:
+        try:
+            os.makedirs(os.path.dirname(cp), exist_ok=True)
+            tmp = cp + f".{os.getpid()}.tmp.npz"
+            np.savez(tmp, n_users=w.n_users, **{f"rp{t}": m[2] for t, m in enumerate(w.mats)},
+                     **{f"ci{t}": m[3] for t, m in enumerate(w.mats)})
+            os.replace(tmp, cp)
+        except Exception:
+            pass
     return w
