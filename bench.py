@@ -97,14 +97,14 @@ def algorithmic_bytes(st, i: int, n_items_a: int) -> float:
             + 4.0 * n_items_a + 12.0 * st.out_nnz[i])
 
 
-def ncu_traffic(workload: str, launches_per_indicator: float):
-    """dram__bytes_read.sum + dram__bytes_write.sum per k_rows launch from the committed `ncu --set full` capture
-    (profiles/r01_k_rows_traffic.json); None when no capture exists for this workload."""
-    p = os.path.join(ROOT, "profiles", "r01_k_rows_traffic.json")
+def ncu_traffic(workload: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the row-kernel launches of ONE indicator, from the committed
+    `ncu --set full` capture (profiles/r02_k_rows_traffic.json) -- quoted only if that capture was taken on this very
+    build of the kernels and on this workload, else None (never a stale figure)."""
     try:
-        d = json.load(open(p))
-        if d["workload"] == workload:
-            return d["dram_bytes_per_indicator"] / max(launches_per_indicator, 1.0)
+        d = json.load(open(os.path.join(ROOT, "profiles", "r02_k_rows_traffic.json")))
+        if d["workload"] == workload and d.get("build") == source_build_id():
+            return d["dram_bytes_per_indicator"]
     except Exception:
         pass
     return None
@@ -121,58 +121,64 @@ def measured_peaks():
 
 
 # ---------------------------------------------------------------------------------------------------------
-def cpu_arm(w: synth.Workload, args, sample: str):
-    """Time the oracle (OpenMP, all host threads) on `sample` of the workload -> (events/s, cores, description, secs)."""
+def _pin_openmp():
+    """Thread placement of the CPU arm, set before libgomp is loaded: one thread per hardware thread, no migration.
+    (torchrun exports OMP_NUM_THREADS=1 to its children; orc_train overrides the count itself.)"""
+    os.environ.setdefault("OMP_PROC_BIND", "spread")
+    os.environ.setdefault("OMP_PLACES", "threads")
+    os.environ.setdefault("OMP_DYNAMIC", "false")
+
+
+def sample_workload(name: str, sample: str, ctx=None, pinned: bool = False):
+    """the workload (sample == "full") or the same generator at a fraction of the users and events.  ctx: generate and
+    ingest on the B200 (seconds); None: numpy on the host (minutes at the 50M-event shapes)."""
+    if sample == "full":
+        return synth.make(name, ctx=ctx, pinned=pinned), f"full {name} workload"
+    f = float(sample)
+    c = synth.CONFIGS[name]
+    sw = synth.make(name, ctx=ctx, pinned=pinned, n_users=max(int(c["n_users"] * f), 1), n_events=max(int(c["n_events"] * f), c["n_types"]))
+    return sw, (f"{name} generator at {f:g} of the users and events ({sw.n_users} users x {sw.n_items} items, "
+                f"{sw.n_events} events, {sw.n_types} types), same item space/k/m")
+
+
+def time_oracle(sw, seed: int, warmup: int, steps: int):
+    """-> (median seconds per train, all step times, threads used).  Times orc_train only (no numpy copies)."""
     from oracle import oracle as orc
     orc.build()
     threads = host_threads()
-    if sample == "full":
-        sw, desc = w, f"full {w.name} workload"
-    else:
-        f = float(sample)
-        sw = synth.make(w.name, n_users=max(int(synth.CONFIGS[w.name]["n_users"] * f), 1),
-                        n_events=max(int(synth.CONFIGS[w.name]["n_events"] * f), w.n_types))
-        desc = (f"{w.name} generator at {f:g} of the users and events ({sw.n_users} users x {sw.n_items} items, "
-                f"{sw.n_events} events, {sw.n_types} types), same item space/k/m")
     mats = [orc.Csr(*m) for m in sw.mats]
     prm = [orc.Params(*p) for p in sw.params]
-    t0 = time.perf_counter()
-    orc.train(mats, prm, args.seed, 0, threads)
-    dt = time.perf_counter() - t0
-    return sw.n_events / dt, threads, desc, dt, sw
+    for _ in range(warmup):
+        orc.time_train(mats, prm, seed, 0, threads)
+    ts = [orc.time_train(mats, prm, seed, 0, threads)[0] for _ in range(max(steps, 1))]
+    return float(np.median(ts)), ts, threads
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    w_cfg = synth.CONFIGS[args.workload]
+    _pin_openmp()
     sample = auto_sample(args.workload) if args.cpu_sample in ("auto", "none") else args.cpu_sample
-    # build the sample once, time W + K oracle runs on it
-    from oracle import oracle as orc
-    orc.build()
-    threads = host_threads()
-    if sample == "full":
-        sw = synth.make(args.workload)
-        desc = f"full {args.workload} workload"
-    else:
-        f = float(sample)
-        sw = synth.make(args.workload, n_users=max(int(w_cfg["n_users"] * f), 1), n_events=max(int(w_cfg["n_events"] * f), 1))
-        desc = (f"{args.workload} generator at {f:g} of the users and events ({sw.n_users} users x {sw.n_items} items, "
-                f"{sw.n_events} events, {sw.n_types} types), same item space/k/m")
-    mats = [orc.Csr(*m) for m in sw.mats]
-    prm = [orc.Params(*p) for p in sw.params]
-    for _ in range(args.warmup):
-        orc.train(mats, prm, args.seed, 0, threads)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        orc.train(mats, prm, args.seed, 0, threads)
-    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    gen_ctx = None
+    try:   # the input generator (not the thing measured) runs on the GPU when the box has one: seconds instead of minutes
+        import universal_recommender_b200 as ur
+        gen_ctx = ur.CcoContext(device=int(os.environ.get("LOCAL_RANK", "0")))
+    except Exception:
+        gen_ctx = None
+    sw, desc = sample_workload(args.workload, sample, gen_ctx)
+    if gen_ctx is not None:
+        sw.mats = [(nr, nc, np.array(rp), np.array(ci)) for (nr, nc, rp, ci) in sw.mats]
+        gen_ctx.close()
+    dt, ts, threads = time_oracle(sw, args.seed, args.warmup, args.steps)
     v = sw.n_events / dt
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
-            "config": {"workload": workload_desc(args.workload), "sample": desc},
+            "config": {"workload": workload_desc(args.workload), "sample": desc,
+                       "timing": "median of the timed steps (orc_train only); min/max in step_ms_min_max",
+                       "step_ms_min_max": [round(min(ts) * 1e3, 1), round(max(ts) * 1e3, 1)],
+                       "omp": {k: os.environ.get(k) for k in ("OMP_PROC_BIND", "OMP_PLACES")}},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc,
                              "note": "CPU restatement of Mahout 0.13.0 SimilarityAnalysis (oracle/cco_oracle.c, OpenMP); the "
                                      "reference's own Mahout-on-Spark path needs a JVM and is not runnable in this image"},
@@ -201,16 +207,90 @@ def workload_desc(name: str) -> str:
 
 
 # ---------------------------------------------------------------------------------------------------------
+class ShmModel:
+    """N > 1 end-to-end leg: the caller of the reference boundary is ONE process (URAlgorithm.train on the Spark driver,
+    URAlgorithm.scala:292-307), so the model is only "back" when every rank's row slice sits in memory that process can
+    read.  Each rank copies its slice into its own region of one /dev/shm segment; after the barrier rank 0 holds views of
+    all of them (a row-partitioned model: exactly what toStringMapRDD iterates over)."""
+
+    def __init__(self, rank: int, world: int, n_types: int, n_items: int, top_k: int, tag: str):
+        self.rank, self.world, self.n_types = rank, world, n_types
+        self.per_ind = 8 * (n_items + 1) + 16 * n_items * top_k + 64
+        self.per_rank = 4096 + n_types * self.per_ind
+        self.path = f"/dev/shm/cco_bench_model_{tag}"
+        if rank == 0:
+            with open(self.path, "wb") as f:
+                f.truncate(self.per_rank * world)
+        self.mm = None
+
+    def open(self):
+        self.mm = np.memmap(self.path, dtype=np.uint8, mode="r+")
+
+    def publish(self, res):
+        """copy this rank's slices (views of the library's pinned result buffers) into the shared segment"""
+        base = self.rank * self.per_rank
+        head = np.zeros(4 * self.n_types, dtype=np.int64)
+        off = base + 4096
+        for i, (rb, re_, nc, rp, ci, ll, cn) in enumerate(res):
+            nnz = int(rp[-1])
+            head[4 * i:4 * i + 4] = (rb, re_, nnz, off)
+            for arr in (rp, ci, ll):
+                b = arr.view(np.uint8)
+                self.mm[off:off + b.size] = b
+                off += (b.size + 63) & ~63
+        self.mm[base:base + head.nbytes] = head.view(np.uint8)
+
+    def model(self):
+        """rank 0: [(row_begin, row_end, row_ptr, col_idx, llr)] per indicator per rank, zero-copy views"""
+        out = []
+        for r in range(self.world):
+            base = r * self.per_rank
+            head = self.mm[base:base + 32 * self.n_types].view(np.int64)
+            sl = []
+            for i in range(self.n_types):
+                rb, re_, nnz, off = (int(x) for x in head[4 * i:4 * i + 4])
+                rp = self.mm[off:off + 8 * (re_ - rb + 1)].view(np.int64)
+                off += (8 * (re_ - rb + 1) + 63) & ~63
+                ci = self.mm[off:off + 4 * nnz].view(np.int32)
+                off += (4 * nnz + 63) & ~63
+                ll = self.mm[off:off + 8 * nnz].view(np.float64)
+                sl.append((rb, re_, rp, ci, ll))
+            out.append(sl)
+        return out
+
+    def close(self):
+        self.mm = None
+        if self.rank == 0:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+
+
+def source_build_id() -> str:
+    """hash of the kernel sources: a committed ncu traffic figure is only quoted for the build it was measured on"""
+    import hashlib
+    h = hashlib.sha1()
+    for f in ("cco_api.cu", "cco_kernels.cuh"):
+        try:
+            h.update(open(os.path.join(ROOT, "universal_recommender_b200", "csrc", f), "rb").read())
+        except OSError:
+            pass
+    return h.hexdigest()[:12]
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
         return
+    _pin_openmp()
     import torch
     import torch.distributed as dist
 
     import universal_recommender_b200 as ur
     from universal_recommender_b200 import _native as N
+    from universal_recommender_b200 import distributed as D
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -244,20 +324,14 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    ctx = ur.CcoContext(device=local_rank, rank=rank, world_size=world, nccl_unique_id=uid)
+    # synthetic events are generated and ingested on the device (cco_synth_ingest; every rank builds the same matrices on
+    # its own GPU) and copied into pinned host memory: what the JNI shim's direct ByteBuffers would hold
     t_gen = time.perf_counter()
-    w = synth.make(args.workload)
+    w = synth.make(args.workload, ctx=ctx, pinned=True)
     t_gen = time.perf_counter() - t_gen
     n_items_a = w.mats[0][1]
-    ctx = ur.CcoContext(device=local_rank, rank=rank, world_size=world, nccl_unique_id=uid)
-
-    # inputs in pinned host memory (what the JNI shim's direct ByteBuffers would be)
-    pinned = []
-    for (nr, nc, rp, ci) in w.mats:
-        prp = ctx.host_array(len(rp), np.int64)
-        pci = ctx.host_array(len(ci), np.int32)
-        prp[:] = rp
-        pci[:] = ci
-        pinned.append((nr, nc, prp, pci))
+    pinned = w.mats
     h2d_bytes = sum(m[2].nbytes + m[3].nbytes for m in pinned)
     flags = ur.FLAG_ASSUME_CANONICAL
 
@@ -288,37 +362,81 @@ def main():
     ctx.free_dataset(ds)
 
     # ---- end to end through cco_train with host buffers ------------------------------------------------------
+    # N > 1: the timed region ends when rank 0 can read the WHOLE model (every rank's row slice) from host memory
+    shm = None
+    if world > 1:
+        shm = ShmModel(rank, world, w.n_types, n_items_a, w.top_k, os.environ.get("MASTER_PORT", "0"))
+        barrier()
+        shm.open()
+
+    def e2e_step():
+        res, h = ctx.train_csr(pinned, w.params, args.seed, flags, keep=True)
+        nbytes = sum(r[3].nbytes + r[4].nbytes + r[5].nbytes + r[6].nbytes for r in res)
+        if shm is not None:
+            shm.publish(res)
+            dist.barrier()
+            if rank == 0:
+                model = shm.model()
+                assert sum(sl[0][1] - sl[0][0] for sl in model) == n_items_a
+        ctx.free_result(h)
+        return nbytes
+
     for _ in range(args.warmup):
-        ctx.train_csr(pinned, w.params, args.seed, flags, copy_arrays=False)
+        e2e_step()
     barrier()
-    ctx.timer_start()
     t0 = time.perf_counter()
     d2h_bytes = 0
     for _ in range(args.steps):
-        res = ctx.train_csr(pinned, w.params, args.seed, flags, copy_arrays=False)
-        d2h_bytes = sum(r[3].nbytes + int(r[3][-1]) * 16 for r in res)
-    ms_e2e = ctx.timer_stop()
+        d2h_bytes = e2e_step()
+    torch.cuda.synchronize()
     wall_e2e = (time.perf_counter() - t0) * 1e3
     barrier()
-    ms_e2e = max_over_ranks(max(ms_e2e, wall_e2e)) / args.steps
+    ms_e2e = max_over_ranks(wall_e2e) / args.steps
     e2e_value = w.n_events / (ms_e2e * 1e-3)
+    d2h_total = int(sum_over_ranks(float(d2h_bytes)))
+
+    # ---- parity gate of this run: the CUDA path against the oracle on the same input --------------
+    sample = auto_sample(args.workload) if args.cpu_sample in ("auto", "none") else args.cpu_sample
+    if sample == "full":
+        sw, sdesc, spinned = w, f"full {w.name} workload", pinned
+    else:
+        sw, sdesc = sample_workload(args.workload, sample, ctx, pinned=True)
+        spinned = sw.mats
+    local = ctx.train_csr(spinned, sw.params, args.seed, flags)
+    parity = None
+    merged = local
+    if world > 1:
+        box = [None] * world if rank == 0 else None
+        dist.gather_object(local, box, dst=0)
+        if rank == 0:
+            merged = []
+            for i in range(sw.n_types):
+                m = D.merge_row_slices([box[r][i] for r in range(world)])    # (n_rows, n_cols, row_ptr, col, llr, count)
+                merged.append((0, m[0], m[1], m[2], m[3], m[4], m[5]))
+    if rank == 0:
+        from oracle import oracle as orc
+        from oracle import parity as par
+        ref = orc.train([orc.Csr(*m) for m in sw.mats], [orc.Params(*p) for p in sw.params], args.seed, 0, host_threads())
+        parity = par.compare(ref, merged, sw.n_users)
+        parity["sample"] = sdesc
+        parity["n_gpus"] = world
 
     # ---- roofline of the fused A'^T B' row kernel (all ranks' rows together) -----------------------------------
     peak, peak_src = measured_peaks()
     alg_total = sum_over_ranks(alg_bytes)
     rows_ms_max = max_over_ranks(rows_ms)
     achieved = alg_total / (rows_ms_max * 1e-3) / 1e9 / max(world, 1) if rows_ms_max > 0 else 0.0
-    n_row_launches = 8 * w.n_types * args.steps   # 8 work-bin launches per indicator (empty bins exit immediately)
-    roofline = {"bound": "hbm", "kernel": "k_rows (fused A'^T B' count + LLR + top-k; work-binned launches per indicator)",
+    n_ind = w.n_types * args.steps
+    roofline = {"bound": "hbm", "kernel": "k_rows (fused A'^T B' count + LLR + top-k; one set of work-binned launches per indicator, "
+                                          "concurrent on separate streams)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                "traffic": ncu_traffic(args.workload, n_row_launches / max(args.steps * w.n_types, 1)), "algorithmic_bytes_per_launch": alg_total / max(world, 1) / n_row_launches,
-                "avg_launch_ms": rows_ms_max / n_row_launches,
-                "note": "per GPU; achieved = SURVEY 8(d) algorithmic bytes of this rank's rows / CUDA-event time of its row-kernel launches "
-                        "(the work bins of one indicator run concurrently on separate streams; the time is the bracket around them)",
+                "traffic": ncu_traffic(args.workload),
+                "algorithmic_bytes_per_indicator": alg_total / max(world, 1) / n_ind,
+                "ms_per_indicator": rows_ms_max / n_ind,
+                "note": "per GPU; one 'launch' = the bin launches of one indicator (they run concurrently, so only their common CUDA-event "
+                        "bracket is a duration); achieved = SURVEY 8(d) algorithmic bytes of this rank's rows / that bracket",
                 "secondary_ceilings": {"llr_cells_evaluated_per_step": int(sum_over_ranks(float(sum(st_last.llr_evaluated)))),
-                                       "fp64_xlogx_per_s_measured": 3.48e11, "smem_atomic_products_per_s_measured": 1.03e12,
-                                       "note": "DESIGN.md 3.2: at C3 nearly every product is a distinct cell, so the fp64 LLR and the "
-                                               "top-k select, not HBM, bound the row kernel"}}
+                                       "fp64_xlogx_per_s_measured": 3.48e11, "smem_atomic_products_per_s_measured": 1.03e12}}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -327,27 +445,34 @@ def main():
                        "l2": "inputs (%.0f MB) larger than the 126 MB L2; no explicit flush" % (h2d_bytes / 1e6)
                        if h2d_bytes > 126e6 else "inputs fit L2 (%.0f MB); no explicit flush" % (h2d_bytes / 1e6),
                        "resident": "value: matrices resident in HBM, indicators left packed in HBM",
+                       "e2e": "cco_train on pinned host CSR -> indicator arrays in host memory" +
+                              (" of rank 0 (every rank's row slice published to one shared segment inside the timed region)" if world > 1 else ""),
                        "products_per_step": int(sum_over_ranks(float(sum(st_last.products)))),
                        "distinct_cells_per_step": int(sum_over_ranks(float(sum(st_last.distinct_cells)))),
-                       "datagen_s": round(t_gen, 1),
+                       "datagen_s": round(t_gen, 1), "build": source_build_id(),
                        "stage_ms_last_resident_step": {"prepare": round(st_last.ms_prepare, 3), "indicators_total": round(st_last.ms_cooccurrence, 3),
                                                        "row_kernels": [round(x, 3) for x in st_last.ms_indicator]}},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": d2h_total,
                     "ms_per_step": ms_e2e},
             "gpu_launches": int(launches),
-            "roofline": roofline}
+            "roofline": roofline,
+            "parity": parity}
     if rank == 0 and world == 1 and args.cpu_sample != "none":
-        sample = auto_sample(args.workload) if args.cpu_sample == "auto" else args.cpu_sample
-        v, cores, desc, secs, _ = cpu_arm(w, args, sample)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc, "seconds": round(secs, 2)}
+        dt, ts, cores = time_oracle(sw, args.seed, 1, 3)
+        line["cpu_baseline"] = {"value": sw.n_events / dt, "unit": UNIT, "cores": cores, "kind": "port", "sample": sdesc,
+                                "seconds": round(dt, 3), "timing": "median of 3 after 1 warm-up"}
     else:
         line["cpu_baseline"] = None
     if rank == 0:
         print(json.dumps(line), flush=True)
+    if shm is not None:
+        shm.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+    if rank == 0 and parity is not None and not parity.get("ok"):
+        raise SystemExit(f"bench.py: PARITY FAILURE against the oracle: {parity}")
 
 
 if __name__ == "__main__":

@@ -192,6 +192,26 @@ typedef struct {
 } cco_events_t;
 int cco_ingest(cco_ctx_t *ctx, int32_t n_types, const cco_events_t *events, int64_t n_users_raw, int32_t min_events_per_user,
                int32_t *user_map, int32_t *const *item_maps, cco_dataset_t **out);
+/*
+ * Bench/test utility: the synthetic Zipf event streams of SURVEY.md 8(d) generated straight into HBM (no host event
+ * arrays), then the same ingest as cco_ingest.  Stream of one event type, bit-identical to synth.py's numpy twin:
+ *   h1 = mix64(mix64(seed) + (e + 1) * 0x9e3779b97f4a7c15), h2 = mix64(h1 ^ 0x6a09e667f3bcc909)      e = 0 .. n_events-1
+ *   user = user_perm[upper_bound(user_cdf, (h1 >> 11) * 2^-53)], item = item_perm[upper_bound(item_cdf, (h2 >> 11) * 2^-53)]
+ * cdf = inclusive, normalised cumulative weights over ranks; perm maps rank -> id.  All arrays are host pointers.
+ * keep_item_space != 0: the item dictionary of every type is its raw id space (identity), not only the ids with an event.
+ */
+typedef struct {
+  int64_t n_events;
+  uint64_t seed;
+  int32_t n_items;
+  int32_t reserved;
+  const double *item_cdf;   /* [n_items] */
+  const int32_t *item_perm; /* [n_items] */
+} cco_synth_type_t;
+int cco_synth_ingest(cco_ctx_t *ctx, int32_t n_types, const cco_synth_type_t *types, int64_t n_users_raw, const double *user_cdf,
+                     const int32_t *user_perm, int32_t min_events_per_user, int32_t keep_item_space, cco_dataset_t **out);
+/* copy matrix i of a resident dataset into caller-provided host arrays ([n_rows + 1] and [nnz], see cco_dataset_shape) */
+int cco_dataset_copy_to_host(const cco_dataset_t *ds, int32_t i, int64_t *row_ptr, int32_t *col_idx);
 int cco_dataset_shape(const cco_dataset_t *ds, int32_t i, int64_t *n_rows, int32_t *n_cols, int64_t *nnz);
 /* test helper: copy matrix i of a resident dataset back to the host (malloc'ed; free with cco_free) */
 int cco_dataset_download(const cco_dataset_t *ds, int32_t i, int64_t **row_ptr, int32_t **col_idx);

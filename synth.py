@@ -2,8 +2,15 @@
 
 item j drawn with p ~ 1/(rank+1)^s_i (s_i = 1.0), user u with p ~ 1/(rank+1)^s_u (s_u = 0.5); ranks are
 mapped to ids by a fixed seeded permutation; events are split equally across event types; type t uses
-seed 1234 + t; all types share the user space, each has its own item space.  Deterministic (numpy PCG64).
-The matrices come out exactly as Preparator would build them: binary, deduplicated, CSR over users.
+seed 1234 + t; all types share the user space, each has its own item space.
+
+The stream is counter based, so the numpy generator here and the CUDA generator of the library
+(cco_synth_ingest, include/cco_b200.h) produce the SAME events bit for bit:
+    h1 = mix64(mix64(seed) + (e + 1) * 0x9e3779b97f4a7c15),  h2 = mix64(h1 ^ 0x6a09e667f3bcc909)        e = 0 .. n-1
+    user = user_perm[searchsorted(user_cdf, (h1 >> 11) * 2^-53, "right")],  item likewise from h2
+make(name) runs on the host (numpy); make(name, ctx=<CcoContext>) generates and ingests on the B200 (seconds instead of
+minutes at the 10M-user shapes) and copies the matrices back.  Either way the matrices come out exactly as Preparator
+would build them: binary, deduplicated, CSR over users, minEventsPerUser applied on the primary event (duplicates count).
 """
 from __future__ import annotations
 
@@ -25,6 +32,7 @@ class Workload:
     min_events_per_user: int | None = None
     mats: list | None = None      # [(n_rows, n_cols, row_ptr int64, col_idx int32)]
     events_per_type: list | None = None
+    dataset: object = None        # resident dataset handle when generated on the device (ctx.free_dataset to release)
 
     @property
     def params(self):
@@ -44,31 +52,59 @@ CONFIGS = {
     "tiny": dict(n_users=300, n_items=120, n_events=6_000, n_types=3),
     "small": dict(n_users=20_000, n_items=5_000, n_events=600_000, n_types=3),
     "C3-tenth": dict(n_users=100_000, n_items=10_000, n_events=5_000_000, n_types=4),
+    # C4 at a tenth of the users and events (same 1M-column item space): the downsampling-dominated parity shape
+    "C4-tenth": dict(n_users=1_000_000, n_items=1_000_000, n_events=50_000_000, n_types=2, min_events_per_user=3),
 }
 
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+_GOLDEN = np.uint64(0x9E3779B97F4A7C15)
+_H2 = np.uint64(0x6A09E667F3BCC909)
 
-def _zipf_cdf(n: int, s: float) -> np.ndarray:
+
+def _mix64(z: np.ndarray) -> np.ndarray:
+    z = z ^ (z >> np.uint64(30))
+    z = z * np.uint64(0xBF58476D1CE4E5B9)
+    z = z ^ (z >> np.uint64(27))
+    z = z * np.uint64(0x94D049BB133111EB)
+    return z ^ (z >> np.uint64(31))
+
+
+def zipf_cdf(n: int, s: float) -> np.ndarray:
     w = 1.0 / np.power(np.arange(1, n + 1, dtype=np.float64), s)
     c = np.cumsum(w)
     return c / c[-1]
 
 
-def _draw(rng: np.random.Generator, cdf: np.ndarray, perm: np.ndarray, n: int) -> np.ndarray:
-    out = np.empty(n, dtype=np.int64)
-    step = 1 << 24
-    for s in range(0, n, step):
-        e = min(n, s + step)
-        out[s:e] = perm[np.searchsorted(cdf, rng.random(e - s), side="right").clip(0, len(cdf) - 1)]
-    return out
+def user_tables(n_users: int, s_user: float = 0.5):
+    """(cdf, perm) of the user space, shared by every event type"""
+    return zipf_cdf(n_users, s_user), np.random.default_rng(99).permutation(n_users).astype(np.int32)
 
 
-def events_for_type(n_users: int, n_items: int, n_events: int, t: int, s_user: float = 0.5, s_item: float = 1.0):
-    """-> (users int64[n_events], items int64[n_events]) raw events of event type t."""
-    rng = np.random.default_rng(1234 + t)
-    user_perm = np.random.default_rng(99).permutation(n_users)     # shared by every type
-    item_perm = np.random.default_rng(1000 + t).permutation(n_items)
-    users = _draw(rng, _zipf_cdf(n_users, s_user), user_perm, n_events)
-    items = _draw(rng, _zipf_cdf(n_items, s_item), item_perm, n_events)
+def item_tables(n_items: int, t: int, s_item: float = 1.0):
+    return zipf_cdf(n_items, s_item), np.random.default_rng(1000 + t).permutation(n_items).astype(np.int32)
+
+
+def type_seed(t: int) -> int:
+    return 1234 + t
+
+
+def events_for_type(n_users: int, n_items: int, n_events: int, t: int, tables=None):
+    """-> (users int64[n_events], items int64[n_events]) raw events of event type t (the numpy twin of k_synth_events)."""
+    ucdf, uperm = tables[0] if tables else user_tables(n_users)
+    icdf, iperm = tables[1] if tables else item_tables(n_items, t)
+    users = np.empty(n_events, dtype=np.int64)
+    items = np.empty(n_events, dtype=np.int64)
+    with np.errstate(over="ignore"):
+        base = _mix64(np.array([type_seed(t)], dtype=np.uint64))[0]
+        step = 1 << 22
+        for s in range(0, n_events, step):
+            e = np.arange(s + 1, min(n_events, s + step) + 1, dtype=np.uint64)
+            h1 = _mix64(base + e * _GOLDEN)
+            h2 = _mix64(h1 ^ _H2)
+            u1 = (h1 >> np.uint64(11)).astype(np.float64) * 2.0 ** -53
+            u2 = (h2 >> np.uint64(11)).astype(np.float64) * 2.0 ** -53
+            users[s:s + len(e)] = uperm[np.minimum(np.searchsorted(ucdf, u1, side="right"), n_users - 1)]
+            items[s:s + len(e)] = iperm[np.minimum(np.searchsorted(icdf, u2, side="right"), n_items - 1)]
     return users, items
 
 
@@ -89,13 +125,62 @@ def _cache_path(name: str, cfg: dict):
     if d == "0" or cfg["n_events"] < 2_000_000:
         return None
     key = "_".join(f"{k}{cfg[k]}" for k in sorted(cfg))
-    return os.path.join(d, f"{name}_{key}.npz")
+    return os.path.join(d, f"v2_{name}_{key}.npz")
 
 
-def make(name: str, **override) -> Workload:
+def _make_host(w: Workload, n_users_raw: int):
+    """numpy path: Preparator semantics on the host.  The item dictionary is the RAW item space (every id of the Zipf
+    support), exactly like the device path below, so both produce identical matrices."""
+    per_type = w.n_events // w.n_types
+    utab = user_tables(n_users_raw)
+    keep_users, new_id = None, None
+    for t in range(w.n_types):
+        users, items = events_for_type(n_users_raw, w.n_items, per_type, t, (utab, item_tables(w.n_items, t)))
+        if t == 0:
+            # Preparator.scala:56-68, 129-132: users with < minEventsPerUser primary events (duplicates count; at least one
+            # event) leave the user dictionary; every event type is then restricted to the passing users (:69-77)
+            cnt = np.bincount(users, minlength=n_users_raw)
+            keep_users = cnt >= max(w.min_events_per_user or 0, 1)
+            new_id = np.cumsum(keep_users) - 1
+            w.n_users = int(keep_users.sum())
+        m = keep_users[users]
+        users, items = new_id[users[m]], items[m]
+        rp, ci = to_binary_csr(users, items, w.n_users, w.n_items)
+        w.mats.append((w.n_users, w.n_items, rp, ci))
+        w.events_per_type.append(per_type)
+
+
+def _make_device(w: Workload, n_users_raw: int, ctx, keep_dataset: bool, pinned: bool):
+    """CUDA path: events generated in HBM (k_synth_events) and ingested there (the cco_ingest pipeline); matrices copied
+    back for the oracle / the end-to-end leg.  Item ids: the device ingest compacts the item dictionary to the items
+    that have an event; the synthetic spaces are remapped back to the raw ids so that host and device agree."""
+    per_type = w.n_events // w.n_types
+    ucdf, uperm = user_tables(n_users_raw)
+    types = []
+    for t in range(w.n_types):
+        icdf, iperm = item_tables(w.n_items, t)
+        types.append((per_type, type_seed(t), icdf, iperm))
+    ds = ctx.synth_dataset(types, n_users_raw, ucdf, uperm, w.min_events_per_user or 0, raw_item_space=True)
+    for t in range(w.n_types):
+        nr, nc, rp, ci = ctx.dataset_to_host(ds, t, pinned=pinned)
+        w.n_users = nr
+        w.mats.append((nr, nc, rp, ci))
+        w.events_per_type.append(per_type)
+    if keep_dataset:
+        w.dataset = ds
+    else:
+        ctx.free_dataset(ds)
+
+
+def make(name: str, ctx=None, keep_dataset: bool = False, pinned: bool = False, **override) -> Workload:
     cfg = dict(CONFIGS[name])
     cfg.update(override)
     w = Workload(name=name, **cfg)
+    n_users_raw = w.n_users
+    w.mats, w.events_per_type = [], []
+    if ctx is not None:
+        _make_device(w, n_users_raw, ctx, keep_dataset, pinned)
+        return w
     cp = _cache_path(name, cfg)
     if cp and os.path.exists(cp):
         try:
@@ -105,26 +190,8 @@ def make(name: str, **override) -> Workload:
             w.events_per_type = [w.n_events // w.n_types] * w.n_types
             return w
         except Exception:
-            pass
-    per_type = w.n_events // w.n_types
-    w.mats, w.events_per_type = [], []
-    keep_users = None
-    n_users_raw = w.n_users
-    for t in range(w.n_types):
-        users, items = events_for_type(n_users_raw, w.n_items, per_type, t)
-        if t == 0 and w.min_events_per_user:
-            # Preparator.scala:56-68: users with < minEventsPerUser primary events (duplicates count) leave the
-            # user dictionary; every event type is then restricted to the passing users (:69-77) and N shrinks.
-            cnt = np.bincount(users, minlength=n_users_raw)
-            keep_users = cnt >= w.min_events_per_user
-            new_id = np.cumsum(keep_users) - 1
-            w.n_users = int(keep_users.sum())
-        if keep_users is not None:
-            m = keep_users[users]
-            users, items = new_id[users[m]], items[m]
-        rp, ci = to_binary_csr(users, items, w.n_users, w.n_items)
-        w.mats.append((w.n_users, w.n_items, rp, ci))
-        w.events_per_type.append(per_type)
+            w.mats, w.events_per_type = [], []
+    _make_host(w, n_users_raw)
     if cp:
         try:
             os.makedirs(os.path.dirname(cp), exist_ok=True)

@@ -70,3 +70,30 @@ def test_plain_c_program_links_against_the_abi(tmp_path):
                     f"-Wl,-rpath,{libdir}"], check=True)
     p = subprocess.run([str(exe)], capture_output=True, text=True)
     assert p.returncode == 0, (p.returncode, p.stdout, p.stderr)
+
+
+def _build_c_consumer(tmp_path):
+    import subprocess
+    from universal_recommender_b200 import _native
+    exe = tmp_path / "c_abi_check"
+    libdir = os.path.dirname(_native.LIB_PATH)
+    subprocess.run(["/usr/bin/gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "abi", "c_abi_check.c"), "-o", str(exe), "-L", libdir, "-lcco_b200",
+                    f"-Wl,-rpath,{libdir}"], check=True)
+    return exe
+
+
+@pytest.mark.gpu
+def test_plain_c_program_trains_on_the_b200(tmp_path):
+    """the non-Python client of the boundary, on the GPU box: its B200 branch (one train through the C ABI) must run"""
+    import subprocess
+    p = subprocess.run([str(_build_c_consumer(tmp_path))], capture_output=True, text=True)
+    assert p.returncode == 0 and "gpu ok" in p.stdout, (p.returncode, p.stdout, p.stderr)
+
+
+def test_jni_shim_compiles():
+    """jni/cco_jni.c is shipped as source (no JDK here): type-check it against the C ABI header and the minimal JNI
+    declarations of tests/abi/jni_min/jni.h, so that the shim cannot rot into pseudo-code."""
+    import subprocess
+    subprocess.run(["/usr/bin/gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "tests", "abi", "jni_min"),
+                    "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "jni", "cco_jni.c")], check=True)

@@ -43,3 +43,25 @@ def test_ingest_edge_cases(orc, ctx):
     ctx.free_dataset(ds)
     with pytest.raises(ur.CcoInvalidArgument):
         ctx.ingest([(np.array([7]), np.array([0], dtype=np.int32), 1)], 3, 0)
+
+
+@pytest.mark.parametrize("name", ["tiny", "small", "C3-tenth"])
+def test_device_generator_matches_numpy_twin(ctx, name):
+    """cco_synth_ingest (events generated and ingested in HBM) and synth.py's numpy path give the same matrices bit for bit:
+    same counter-based stream, same Preparator semantics (user dictionary from the primary events, dedup)."""
+    import synth
+    host = synth.make(name)
+    dev = synth.make(name, ctx=ctx)
+    assert host.n_users == dev.n_users
+    for (nr, nc, rp, ci), (dnr, dnc, drp, dci) in zip(host.mats, dev.mats):
+        assert (nr, nc) == (dnr, dnc)
+        assert np.array_equal(rp, drp) and np.array_equal(ci, dci)
+
+
+def test_device_generator_min_events_filter(ctx):
+    import synth
+    host = synth.make("small", min_events_per_user=12)
+    dev = synth.make("small", ctx=ctx, min_events_per_user=12)
+    assert host.n_users == dev.n_users < 20_000
+    for h, d in zip(host.mats, dev.mats):
+        assert np.array_equal(h[2], d[2]) and np.array_equal(h[3], d[3])

@@ -32,7 +32,7 @@ def oracle_train(orc, mats, params, seed, flags=0):
 # ---- synthetic workloads (sizes the oracle finishes in seconds) -------------------------------------------------------
 @pytest.mark.parametrize("name", ["tiny", "small", "C2", "C3-tenth"])
 def test_synthetic_parity(orc, ctx, name):
-    w = synth.make(name)
+    w = synth.make(name, ctx=ctx)                 # generated + ingested on the device (cco_synth_ingest)
     got = ctx.train_csr(w.mats, w.params, seed=42)
     ref = oracle_train(orc, w.mats, w.params, 42)
     assert_indicators_equal(ref, got, name)
@@ -248,11 +248,15 @@ def test_dataset_api_matches_one_shot(ctx):
     assert max(np.diff(three[0][3])) <= 7
 
 
-# ---- full size: BASELINE.json configs[2] (C3), size-independent properties --------------------------------------------------------------
-def test_c3_full_size_properties(ctx):
-    w = synth.make("C3")
+# ---- full size: BASELINE.json configs[2] (C3) against the oracle, plus size-independent properties -----------------------------------
+def test_c3_full_size_against_oracle(orc, ctx):
+    from oracle import parity as par
+    w = synth.make("C3", ctx=ctx)
     res = ctx.train_csr(w.mats, w.params, seed=42, flags=ur.FLAG_ASSUME_CANONICAL)
     st = ctx.last_stats
+    ref = oracle_train(orc, w.mats, w.params, 42)
+    par.assert_ok(par.compare(ref, res, w.n_users), "C3 full size")
+    assert st.products == [r.products for r in ref] and st.distinct_cells == [r.distinct_cells for r in ref]
     n_items = w.n_items
     for i, (rb, re_, nc, rp, ci, ll, cn) in enumerate(res):
         assert (rb, re_, nc) == (0, n_items, n_items)
@@ -267,15 +271,58 @@ def test_c3_full_size_properties(ctx):
         assert (ci[1:][tie] > ci[:-1][tie]).all()
         if i == 0:
             assert (ci != same_row).all()                       # A'^T A': the diagonal is excluded
-    # checksum of checksums: products reported by the device == sum_u degA'(u) * degB'(u) recomputed on the host from
-    # an independent device downsample of each matrix
-    degs = []
-    for (nr, nc, rp, ci) in w.mats[:2]:
-        grp, _, _, _ = ctx.debug_downsample(nr, nc, rp, ci, 500, 42, ur.FLAG_ASSUME_CANONICAL)
-        degs.append(np.diff(grp))
-    assert st.products[0] == int((degs[0].astype(np.int64) ** 2).sum())
-    assert st.products[1] == int((degs[0].astype(np.int64) * degs[1]).sum())
     # idempotence
     again = ctx.train_csr(w.mats, w.params, seed=42, flags=ur.FLAG_ASSUME_CANONICAL)
     for x, y in zip(res, again):
         assert all(np.array_equal(p, q) for p, q in zip(x[3:], y[3:]))
+
+
+def test_downsampling_dominated_million_column_shape(orc, ctx):
+    """BASELINE.json configs[3] (C4) at a tenth of the users and events: 1M-column item space (hashed tables in every bin,
+    12 count bits), Zipf-hot columns far above m = 500 (column downsampling removes most of their entries), users above m,
+    minEventsPerUser = 3 applied when the CSR is built -- against the oracle, bit for bit."""
+    from oracle import parity as par
+    w = synth.make("C4-tenth", ctx=ctx)
+    assert w.n_users < 1_000_000                                  # the duplicate-counting minEventsPerUser filter bit
+    raw_col = np.bincount(w.mats[0][3], minlength=w.n_items)
+    assert raw_col.max() > 50 * 500 and (raw_col > 500).sum() > 1000
+    res = ctx.train_csr(w.mats, w.params, seed=42, flags=ur.FLAG_ASSUME_CANONICAL)
+    st = ctx.last_stats
+    ref = oracle_train(orc, w.mats, w.params, 42)
+    par.assert_ok(par.compare(ref, res, w.n_users), "C4-tenth")
+    assert st.nnz_downsampled == [r.nnz_b for r in ref]
+    assert st.nnz_downsampled[0] < 0.8 * len(w.mats[0][3])       # downsampling really dominates
+    # intdiv row rate (the literal Mahout recall) on the same shape
+    got = ctx.train_csr(w.mats, w.params, seed=42, flags=ur.FLAG_ASSUME_CANONICAL | ur.FLAG_ROWRATE_INTDIV)
+    par.assert_ok(par.compare(oracle_train(orc, w.mats, w.params, 42, ur.FLAG_ROWRATE_INTDIV), got, w.n_users), "C4-tenth intdiv")
+
+
+# ---- documented limits (include/cco_b200.h "Limits"): clean errors, never wrong results -------------------------------------------
+def _csr_from_rows(rows, nc):
+    rp = np.zeros(len(rows) + 1, dtype=np.int64)
+    np.cumsum([len(r) for r in rows], out=rp[1:])
+    return (len(rows), nc, rp, np.array([c for r in rows for c in r], dtype=np.int32))
+
+
+def test_packed_word_limit_is_a_clean_error_and_downsampling_lifts_it(orc, ctx):
+    # 3M columns leave 10 count bits in the packed (key, count) word.  One (a, b) pair co-occurs 3000 times: without
+    # downsampling that count does not fit -> CCO_E_UNSUPPORTED with a message that names the remedy; with the reference's
+    # default m = 500 every marginal (hence every count) is <= ~560 and the same matrices train and match the oracle.
+    rng = np.random.default_rng(21)
+    nu, ia, ib = 5000, 40, 3_000_000
+    hot_b = [7, 2_999_999, 1_500_001]
+    a_rows, b_rows = [], []
+    for u in range(nu):
+        a = set(rng.integers(1, ia, 2).tolist())
+        b = set(rng.integers(0, ib, 6).tolist())
+        if u < 3000:
+            a.add(0)
+            b.update(hot_b)
+        a_rows.append(sorted(a))
+        b_rows.append(sorted(b))
+    mats = [_csr_from_rows(a_rows, ia), _csr_from_rows(b_rows, ib)]
+    with pytest.raises(ur.CcoError) as e:
+        ctx.train_csr(mats, [(10 ** 6, 50, None)] * 2, seed=2)
+    assert e.value.status == -6 and "maxItemsPerUser" in str(e.value)
+    params = [(500, 50, None), (500, 50, None)]
+    assert_indicators_equal(oracle_train(orc, mats, params, 2), ctx.train_csr(mats, params, seed=2), "3M columns, m=500")

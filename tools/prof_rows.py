@@ -5,8 +5,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import synth
 import universal_recommender_b200 as ur
 from universal_recommender_b200 import _native as N
-w = synth.make(sys.argv[1] if len(sys.argv) > 1 else "C3")
 ctx = ur.CcoContext()
+w = synth.make(sys.argv[1] if len(sys.argv) > 1 else "C3", ctx=ctx)
 ds = ctx.upload(w.mats, ur.FLAG_ASSUME_CANONICAL)
 for it in range(int(sys.argv[2]) if len(sys.argv) > 2 else 2):
     ctx.train_dataset(ds, w.params, 42, ur.FLAG_ASSUME_CANONICAL | N.FLAG_RESULT_ON_DEVICE, copy_arrays=False)

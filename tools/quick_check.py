@@ -8,8 +8,8 @@ import universal_recommender_b200 as ur
 
 name = sys.argv[1] if len(sys.argv) > 1 else "tiny"
 do_oracle = (len(sys.argv) <= 2) or sys.argv[2] != "nooracle"
-t0 = time.time(); w = synth.make(name); print(f"{name}: generated in {time.time()-t0:.1f}s; nnz per type {[int(m[2][-1]) for m in w.mats]}")
-ctx = ur.CcoContext()
+t0 = time.time(); ctx = ur.CcoContext()
+w = synth.make(name, ctx=ctx); print(f"{name}: generated in {time.time()-t0:.1f}s; nnz per type {[int(m[2][-1]) for m in w.mats]}")
 for it in range(int(os.environ.get("QC_ITERS", "3"))):
     t0 = time.time(); res = ctx.train_csr(w.mats, w.params, seed=42, flags=ur.FLAG_ASSUME_CANONICAL); dt = time.time() - t0
     st = ctx.last_stats

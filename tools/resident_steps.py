@@ -4,8 +4,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import synth
 import universal_recommender_b200 as ur
 from universal_recommender_b200 import _native as N
-w = synth.make(sys.argv[1] if len(sys.argv) > 1 else "C3")
 ctx = ur.CcoContext()
+w = synth.make(sys.argv[1] if len(sys.argv) > 1 else "C3", ctx=ctx)
 ds = ctx.upload(w.mats, ur.FLAG_ASSUME_CANONICAL)
 for flags, name in ((ur.FLAG_ASSUME_CANONICAL | N.FLAG_RESULT_ON_DEVICE, "resident/no-D2H"), (ur.FLAG_ASSUME_CANONICAL, "resident/with-D2H")):
     for it in range(6):

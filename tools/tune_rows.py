@@ -5,8 +5,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import synth
 import universal_recommender_b200 as ur
-w = synth.make(sys.argv[1] if len(sys.argv) > 1 else "C3")
 ctx = ur.CcoContext()
+w = synth.make(sys.argv[1] if len(sys.argv) > 1 else "C3", ctx=ctx)
 ds = ctx.upload(w.mats, ur.FLAG_ASSUME_CANONICAL)
 variants = [{}, {"CCO_TUNE_GRID_MULT": "2"}, {"CCO_TUNE_GRID_MULT": "4"}, {"CCO_TUNE_CAP": "66"}, {"CCO_TUNE_CAP": "75"},
             {"CCO_TUNE_WARP_CTA": "128"}, {"CCO_TUNE_WARP_CTA": "256"}, {"CCO_TUNE_WARP_CBUF": "128"}, {"CCO_TUNE_SERIAL": "1"},

@@ -11,8 +11,12 @@
 #include <string.h>
 
 #include <algorithm>
+#include <functional>
 #include <cub/cub.cuh>
+#include <nvtx3/nvToolsExt.h>
+#include <condition_variable>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "../../include/cco_b200.h"
@@ -53,6 +57,7 @@ struct Nccl {
   void *h = nullptr;
   int (*GetUniqueId)(ncclUniqueId *) = nullptr;
   int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  int (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
   int (*CommDestroy)(ncclComm_t) = nullptr;
   int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
@@ -74,6 +79,7 @@ static int load_nccl() {
   if (!g_nccl.field) return set_error(CCO_E_NCCL, "libnccl: missing symbol %s", name);
   SYM(GetUniqueId, "ncclGetUniqueId")
   SYM(CommInitRank, "ncclCommInitRank")
+  SYM(CommInitAll, "ncclCommInitAll")
   SYM(CommDestroy, "ncclCommDestroy")
   SYM(AllReduce, "ncclAllReduce")
   SYM(AllGather, "ncclAllGather")
@@ -85,7 +91,7 @@ static int load_nccl() {
   g_nccl.h = h;
   return CCO_OK;
 }
-constexpr int kNcclInt32 = 2, kNcclUint32 = 3, kNcclSum = 0;  // ncclInt32, ncclUint32, ncclSum (nccl.h enum values)
+constexpr int kNcclInt32 = 2, kNcclUint32 = 3, kNcclSum = 0, kNcclMax = 2;  // ncclInt32, ncclUint32, ncclSum, ncclMax (nccl.h enum values)
 
 }  // namespace cco
 
@@ -98,6 +104,30 @@ struct PinnedBuf {
   void *p;
   size_t cap;
   bool used;
+};
+
+// shared by the per-GPU member contexts of a group (single-process multi-GPU) context
+struct GroupShared {
+  int world = 0;
+  std::mutex mu;
+  std::condition_variable cv;
+  int arrived = 0;
+  unsigned long long generation = 0;
+  std::vector<long long> totals;   // per rank: kept cells of the indicator being merged
+  struct cco_result *merged = nullptr;
+  int status = 0;                  // first failure of any member thread
+  char err[512] = "";
+  void barrier() {
+    std::unique_lock<std::mutex> lk(mu);
+    const unsigned long long g = generation;
+    if (++arrived == world) {
+      arrived = 0;
+      ++generation;
+      cv.notify_all();
+    } else {
+      cv.wait(lk, [&] { return generation != g; });
+    }
+  }
 };
 
 struct cco_ctx {
@@ -114,15 +144,36 @@ struct cco_ctx {
   std::mutex mu;
   ncclComm_t comm = nullptr;
   int launches = 0;
-  // mailbox for small device -> host results (mapped pinned memory written by k_mail_bytes)
+  // mailbox for small device -> host results (mapped pinned memory written by k_mail_bytes).  Records are closed into
+  // groups; a group is complete when its event has fired, so the host can wait for indicator i's numbers while the GPU
+  // already runs indicator i + 1 (no stream-wide synchronisation).
   unsigned char *mail_h = nullptr, *mail_d = nullptr;
   size_t mail_used = 0;
-  struct MailItem { void *dst; size_t off, n; };
+  struct MailItem { void *dst; size_t off, n; int group; };
   std::vector<MailItem> mail_pending;
+  std::vector<cudaEvent_t> mail_ev;
+  int mail_group = 0;
+  // optional caller-provided result arena (cco_config_t.result_arena): results are bump-allocated from it, e.g. a
+  // shared-memory segment another process maps, so that no copy separates this rank's slice from the reader
+  unsigned char *arena = nullptr;
+  size_t arena_bytes = 0, arena_used = 0;
+  int arena_live = 0;
+  bool arena_registered = false;
+  // group context: the leader owns one member context per GPU (members[0]->device = devices[0], ...)
+  std::vector<cco_ctx *> members;
+  GroupShared *gshared = nullptr;   // set on members
 
   void *pinned_get(size_t bytes) {
     std::lock_guard<std::mutex> lk(mu);
     if (bytes == 0) bytes = 16;
+    if (arena) {
+      const size_t off = (arena_used + 255) & ~(size_t)255;
+      if (off + bytes <= arena_bytes) {
+        arena_used = off + bytes;
+        ++arena_live;
+        return arena + off;
+      }
+    }
     int best = -1;
     for (size_t i = 0; i < pinned.size(); ++i)
       if (!pinned[i].used && pinned[i].cap >= bytes && (best < 0 || pinned[i].cap < pinned[best].cap)) best = (int)i;
@@ -132,12 +183,16 @@ struct cco_ctx {
     }
     void *p = nullptr;
     size_t cap = (bytes + (1u << 20) - 1) & ~((size_t)(1u << 20) - 1);
-    if (cudaHostAlloc(&p, cap, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    if (cudaHostAlloc(&p, cap, cudaHostAllocPortable) != cudaSuccess) return nullptr;
     pinned.push_back({p, cap, true});
     return p;
   }
   void pinned_put(void *p) {
     std::lock_guard<std::mutex> lk(mu);
+    if (arena && (unsigned char *)p >= arena && (unsigned char *)p < arena + arena_bytes) {
+      if (--arena_live <= 0) { arena_live = 0; arena_used = 0; }   // every result freed: the arena starts over
+      return;
+    }
     for (auto &b : pinned)
       if (b.p == p) b.used = false;
   }
@@ -151,15 +206,22 @@ struct ResultMat {
   double *llr = nullptr;
   int32_t *cnt = nullptr;
 };
+// A dataset holds, per event type, the block of user rows this context works on: the whole matrix on a single GPU,
+// this rank's user block [row_base, row_base + n_local) in a multi-GPU job (each GPU uploads 1/N of the rows).
 struct cco_dataset {
   cco_ctx *ctx = nullptr;
   int n_mats = 0;
-  long long n_users = 0;
-  std::vector<long long> n_cols, nnz;
-  std::vector<long long *> rp;   // device, int64 [n_users+1]
-  std::vector<int32_t *> col;    // device
+  long long n_users = 0;           // U, global
+  long long row_base = 0, n_local = 0;
+  std::vector<long long> n_cols, nnz;   // nnz: stored entries of the WHOLE matrix as handed in
+  std::vector<long long *> rp;   // device, indexable by local row 0 .. n_local (values index `col`)
+  std::vector<int32_t *> col;    // device, indexable by the values of rp
+  std::vector<void *> rp_alloc, col_alloc;   // what to free (rp/col may be offset views of these)
+  std::vector<long long> block_cap;          // per matrix: largest raw entry count of any rank's user block
   std::vector<cudaEvent_t> ready;  // per matrix: host->device copy finished (copy stream)
   bool h2d_pending = false;        // uploaded asynchronously: ms_h2d is read when the train joins
+  bool validated = false;          // k_check_rows has run (and the rows are canonical)
+  bool whole = false;              // rp_alloc / col_alloc hold the WHOLE matrices (device-built datasets, single-GPU uploads)
   float ms_h2d = 0;
 };
 
@@ -199,6 +261,10 @@ struct Arena {
   }
 };
 
+// NVTX ranges per stage (tracing); header-only NVTX3, a no-op unless a profiler is attached
+static inline void nvtx_push(const char *name) { nvtxRangePushA(name); }
+static inline void nvtx_pop() { nvtxRangePop(); }
+
 static inline int grid_for(long long work_items, int block, int sm_count, int waves = 8) {
   long long g = (work_items + block - 1) / block;
   long long cap = (long long)sm_count * waves;
@@ -208,30 +274,56 @@ static inline int grid_for(long long work_items, int block, int sm_count, int wa
 }
 
 constexpr size_t kMailBytes = 1 << 16;
-// enqueue "copy n bytes from device to *dst_host"; the value is there after mail_wait()
+// enqueue "copy n bytes from device to *dst_host"; the value is there after the group it belongs to has been waited for
 static int mail_fetch(cco_ctx *c, void *dst_host, const void *src_dev, size_t n) {
   size_t off = (c->mail_used + 7) & ~(size_t)7;
   if (off + n > kMailBytes) return set_error(CCO_E_CUDA, "internal: mailbox overflow");
   k_mail_bytes<<<1, 128, 0, c->stream>>>(c->mail_d + off, (const unsigned char *)src_dev, (int)n);
-  c->mail_pending.push_back({dst_host, off, n});
+  c->mail_pending.push_back({dst_host, off, n, c->mail_group});
   c->mail_used = off + n;
   return CCO_OK;
 }
-static int mail_wait(cco_ctx *c) {
-  CK(cudaStreamSynchronize(c->stream));
-  CK(cudaGetLastError());
-  for (auto &m : c->mail_pending) memcpy(m.dst, c->mail_h + m.off, m.n);
-  c->mail_pending.clear();
-  c->mail_used = 0;
+// close the current group: everything fetched so far is complete once the returned group's event has fired
+static int mail_close(cco_ctx *c, int *group) {
+  const int g = c->mail_group;
+  while ((int)c->mail_ev.size() <= g) {
+    cudaEvent_t e;
+    CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->mail_ev.push_back(e);
+  }
+  CK(cudaEventRecord(c->mail_ev[g], c->stream));
+  c->mail_group = g + 1;
+  if (group) *group = g;
   return CCO_OK;
 }
+static int mail_wait_group(cco_ctx *c, int g) {
+  CK(cudaEventSynchronize(c->mail_ev[g]));
+  CK(cudaGetLastError());
+  for (auto &m : c->mail_pending)
+    if (m.group == g) memcpy(m.dst, c->mail_h + m.off, m.n);
+  return CCO_OK;
+}
+static void mail_reset(cco_ctx *c) {
+  c->mail_pending.clear();
+  c->mail_used = 0;
+  c->mail_group = 0;
+}
+// close + wait: the host needs the values now
+static int mail_wait(cco_ctx *c) {
+  int g = 0;
+  CKR(mail_close(c, &g));
+  return mail_wait_group(c, g);
+}
 
-struct DevRaw {  // a matrix as uploaded (int64 row_ptr like the host)
-  long long n_rows = 0;
+struct DevRaw {  // a block of user rows of a matrix as uploaded (int64 row_ptr like the host)
+  long long n_rows = 0;     // rows of the block (n_local)
+  long long row_base = 0;   // global index of its first row
   int32_t n_cols = 0;
-  long long nnz = 0;
-  long long *rp = nullptr;
-  int32_t *col = nullptr;
+  long long nnz = 0;        // entries of the block
+  long long nnz_cap = 0;    // entries of the whole matrix (upper bound for the sampled matrix)
+  long long q_base = 0;     // value of rp[0] (host-known): a rank's block keeps the caller's absolute offsets
+  long long *rp = nullptr;  // indexable by local row
+  int32_t *col = nullptr;   // indexable by rp values
 };
 struct DevMat {  // after canonicalise + downsample
   long long n_rows = 0;
@@ -287,10 +379,13 @@ static int canonicalize_device(cco_ctx *c, Arena &ar, DevRaw &m) {
   CKR(exclusive_sum_u32(c, ar, flag, pos, m.nnz + 1));
   uint32_t n_unique = 0;
   CK(cudaMemcpyAsync(&n_unique, pos + m.nnz, 4, cudaMemcpyDeviceToHost, c->stream));
-  k_unique_scatter<<<grid_for(m.nnz, 256, c->sm_count), 256, 0, c->stream>>>(m.nnz, sorted, flag, pos, other, m.col);
+  // the canonical block is rewritten 0-based at the start of its own column storage
+  k_unique_scatter<<<grid_for(m.nnz, 256, c->sm_count), 256, 0, c->stream>>>(m.nnz, sorted, flag, pos, other, m.col + m.q_base);
   CK(cudaStreamSynchronize(c->stream));
   k_rowptr_from_keys<<<grid_for(m.n_rows + 1, 256, c->sm_count), 256, 0, c->stream>>>(m.n_rows, n_unique, other, m.rp);
   c->launches += 2;
+  m.col += m.q_base;
+  m.q_base = 0;
   m.nnz = n_unique;
   CK(cudaGetLastError());
   ar.release(flag);
@@ -300,7 +395,7 @@ static int canonicalize_device(cco_ctx *c, Arena &ar, DevRaw &m) {
   return CCO_OK;
 }
 
-// sampleDownAndBinarize of one uploaded matrix (raw column counts already final in raw_counts)
+// sampleDownAndBinarize of one whole matrix on this GPU (raw column counts already final in raw_counts)
 static int downsample_device(cco_ctx *c, Arena &ar, const DevRaw &raw, const int32_t *raw_counts, int32_t m,
                              int32_t seed, uint32_t flags, DevMat *out) {
   out->n_rows = raw.n_rows;
@@ -308,81 +403,94 @@ static int downsample_device(cco_ctx *c, Arena &ar, const DevRaw &raw, const int
   uint32_t *kept;
   CKR(ar.alloc(&kept, raw.n_rows + 1));
   CKR(ar.alloc(&out->rp, raw.n_rows + 1));
-  CKR(ar.alloc(&out->marg, std::max<int32_t>(raw.n_cols, 1)));
+  if (!out->marg) CKR(ar.alloc(&out->marg, std::max<int32_t>(raw.n_cols, 1)));
   CKR(ar.alloc(&out->col, std::max<long long>(raw.nnz, 1)));
   CK(cudaMemsetAsync(out->marg, 0, sizeof(int32_t) * std::max<int32_t>(raw.n_cols, 1), c->stream));
   CK(cudaMemsetAsync(kept + raw.n_rows, 0, 4, c->stream));
   int g = grid_for(raw.n_rows * kSG, 256, c->sm_count);
-  k_downsample_count<<<g, 256, 0, c->stream>>>(0, raw.n_rows, raw.rp, raw.col, raw_counts, m, seed, flags, kept, out->marg);
+  k_downsample_count<<<g, 256, 0, c->stream>>>(raw.n_rows, 0, raw.rp, raw.col, raw_counts, m, seed, flags, kept, out->marg);
   CKR(exclusive_sum_u32(c, ar, kept, out->rp, raw.n_rows + 1));
-  k_downsample_write<<<g, 256, 0, c->stream>>>(0, raw.n_rows, raw.rp, raw.col, raw_counts, m, seed, flags, out->rp, out->col);
+  k_downsample_write<<<g, 256, 0, c->stream>>>(raw.n_rows, 0, raw.rp, raw.col, raw_counts, m, seed, flags, out->rp, nullptr, out->col);
   c->launches += 2;
   CK(cudaGetLastError());
   ar.release(kept);
   return CCO_OK;
 }
 
-// Multi-GPU form of sampleDownAndBinarize: rank r samples only its block of users, the per-row kept counts are
-// all-gathered (so every rank derives the same row_ptr), each rank writes its block of the compacted column array at
-// its global offset and the blocks are exchanged with grouped broadcasts over NVLink.  The post-sample column
-// marginals are then a local histogram of the gathered matrix.  All matrices go through phase 1 before the single
-// host synchronisation (block offsets), then ONE NCCL group moves every block of every matrix.
-static int downsample_sharded_all(cco_ctx *c, Arena &ar, const std::vector<DevRaw> &raw, const int32_t *raw_counts,
-                                  const std::vector<long long> &col_off, const cco_indicator_params_t *params, int32_t seed,
-                                  uint32_t flags, std::vector<DevMat> &dm) {
+static int nccl_check(int rc, const char *what) {
+  if (rc != 0) return set_error(CCO_E_NCCL, "%s: %s", what, g_nccl.GetErrorString(rc));
+  return CCO_OK;
+}
+
+// Multi-GPU form of sampleDownAndBinarize.  Rank r holds (and samples) only its block of users.  Four collectives over
+// NVLink per train, no host round trip anywhere:
+//   (1) [caller] all-reduce of the raw column counts            -> the sampling rates
+//   (2) all-gather of the per-user kept counts (all matrices)   -> every rank scans the identical row_ptr
+//   (3) all-reduce of the post-sample column counts             -> marginals (nothing is re-counted on the gathered matrix)
+//   (4) all-gather of the sampled column blocks, each padded to the largest raw block (a size the host knows from the
+//       caller's row_ptr), then a pack kernel that reads the true block lengths from row_ptr on the device.
+static int downsample_sharded_all(cco_ctx *c, Arena &ar, const std::vector<DevRaw> &raw, const std::vector<long long> &block_cap,
+                                  long long U, const int32_t *raw_counts, int32_t *marg_all, const std::vector<long long> &col_off,
+                                  const cco_indicator_params_t *params, int32_t seed, uint32_t flags, std::vector<DevMat> &dm) {
   cudaStream_t s = c->stream;
   const int W = c->world, r = c->rank, n_mats = (int)raw.size();
-  const long long U = raw[0].n_rows;
   const long long S = (U + W - 1) / W;
-  const long long u_lo = std::min<long long>((long long)r * S, U), u_hi = std::min<long long>(u_lo + S, U);
-  const int g = grid_for(std::max<long long>(u_hi - u_lo, 1) * kSG, 256, c->sm_count);
-  std::vector<std::vector<uint32_t>> offs(n_mats, std::vector<uint32_t>((size_t)W + 1, 0));
+  const long long n_local = raw[0].n_rows, row_base = raw[0].row_base;
+  const int g = grid_for(std::max<long long>(n_local, 1) * kSG, 256, c->sm_count);
+  std::vector<uint32_t *> kept(n_mats, nullptr);
   for (int i = 0; i < n_mats; ++i) {
     DevMat *out = &dm[i];
     out->n_rows = U;
     out->n_cols = raw[i].n_cols;
-    uint32_t *kept;
-    CKR(ar.alloc(&kept, (size_t)(W * S + 1)));
+    out->marg = marg_all + col_off[i];
+    CKR(ar.alloc(&kept[i], (size_t)(W * S + 1)));
     CKR(ar.alloc(&out->rp, U + 1));
-    CKR(ar.alloc(&out->marg, std::max<int32_t>(raw[i].n_cols, 1)));
-    CKR(ar.alloc(&out->col, std::max<long long>(raw[i].nnz, 1)));
-    CK(cudaMemsetAsync(out->marg, 0, sizeof(int32_t) * std::max<int32_t>(raw[i].n_cols, 1), s));
-    CK(cudaMemsetAsync(kept, 0, sizeof(uint32_t) * (size_t)(W * S + 1), s));
-    const int32_t m = params[i].max_interactions;
-    const int32_t *rc_i = raw_counts + col_off[i];
-    if (u_hi > u_lo) {
-      k_downsample_count<<<g, 256, 0, s>>>(u_lo, u_hi, raw[i].rp, raw[i].col, rc_i, m, seed, flags, kept, nullptr);
+    CK(cudaMemsetAsync(kept[i], 0, sizeof(uint32_t) * (size_t)(W * S + 1), s));
+    if (n_local > 0) {
+      k_downsample_count<<<g, 256, 0, s>>>(n_local, row_base, raw[i].rp, raw[i].col, raw_counts + col_off[i], params[i].max_interactions,
+                                           seed, flags, kept[i], out->marg);
       c->launches++;
     }
-    int rc = g_nccl.AllGather(kept + (size_t)r * S, kept, (size_t)S, kNcclUint32, c->comm, s);
-    if (rc != 0) return set_error(CCO_E_NCCL, "ncclAllGather: %s", g_nccl.GetErrorString(rc));
-    CKR(exclusive_sum_u32(c, ar, kept, out->rp, U + 1));
-    if (u_hi > u_lo) {
-      k_downsample_write<<<g, 256, 0, s>>>(u_lo, u_hi, raw[i].rp, raw[i].col, rc_i, m, seed, flags, out->rp, out->col);
-      c->launches++;
-    }
-    for (int q = 0; q <= W; ++q) CKR(mail_fetch(c, &offs[i][q], out->rp + std::min<long long>((long long)q * S, U), 4));
-    ar.release(kept);
   }
-  CKR(mail_wait(c));
-  g_nccl.GroupStart();
-  for (int i = 0; i < n_mats; ++i)
-    for (int q = 0; q < W; ++q) {
-      const size_t cnt = offs[i][q + 1] - offs[i][q];
-      if (cnt == 0) continue;
-      int rc = g_nccl.Broadcast(dm[i].col + offs[i][q], dm[i].col + offs[i][q], cnt, kNcclInt32, q, c->comm, s);
-      if (rc != 0) {
-        g_nccl.GroupEnd();
-        return set_error(CCO_E_NCCL, "ncclBroadcast: %s", g_nccl.GetErrorString(rc));
-      }
+  if (S > 0) {
+    g_nccl.GroupStart();
+    for (int i = 0; i < n_mats; ++i) {
+      int rc = g_nccl.AllGather(kept[i] + (size_t)r * S, kept[i], (size_t)S, kNcclUint32, c->comm, s);
+      if (rc != 0) { g_nccl.GroupEnd(); return nccl_check(rc, "ncclAllGather(kept counts)"); }
     }
-  int rc = g_nccl.GroupEnd();
-  if (rc != 0) return set_error(CCO_E_NCCL, "ncclGroupEnd: %s", g_nccl.GetErrorString(rc));
-  for (int i = 0; i < n_mats; ++i)
-    if (offs[i][W] > 0) {
-      k_col_histogram_u32<<<grid_for(offs[i][W], 256, c->sm_count), 256, 0, s>>>(dm[i].rp, dm[i].rp + U, dm[i].col, dm[i].marg);
+    CKR(nccl_check(g_nccl.GroupEnd(), "ncclGroupEnd(kept counts)"));
+  }
+  if (col_off[n_mats] > 0)
+    CKR(nccl_check(g_nccl.AllReduce(marg_all, marg_all, (size_t)col_off[n_mats], kNcclInt32, kNcclSum, c->comm, s), "ncclAllReduce(marginals)"));
+  std::vector<int32_t *> gathered(n_mats, nullptr);
+  for (int i = 0; i < n_mats; ++i) {
+    CKR(exclusive_sum_u32(c, ar, kept[i], dm[i].rp, U + 1));
+    ar.release(kept[i]);
+    const long long cap = block_cap[i];
+    CKR(ar.alloc(&dm[i].col, std::max<long long>(raw[i].nnz_cap, 1)));
+    if (cap == 0) continue;
+    CKR(ar.alloc(&gathered[i], (size_t)(cap * W)));
+    if (n_local > 0) {
+      // this rank's block goes straight into its slot of the gather buffer, relative to the block's first entry
+      k_downsample_write<<<g, 256, 0, s>>>(n_local, row_base, raw[i].rp, raw[i].col, raw_counts + col_off[i], params[i].max_interactions,
+                                           seed, flags, dm[i].rp, dm[i].rp + row_base, gathered[i] + (size_t)r * cap);
       c->launches++;
     }
+  }
+  g_nccl.GroupStart();
+  for (int i = 0; i < n_mats; ++i) {
+    if (!gathered[i]) continue;
+    int rc = g_nccl.AllGather(gathered[i] + (size_t)r * block_cap[i], gathered[i], (size_t)block_cap[i], kNcclInt32, c->comm, s);
+    if (rc != 0) { g_nccl.GroupEnd(); return nccl_check(rc, "ncclAllGather(column blocks)"); }
+  }
+  CKR(nccl_check(g_nccl.GroupEnd(), "ncclGroupEnd(column blocks)"));
+  for (int i = 0; i < n_mats; ++i) {
+    if (!gathered[i]) continue;
+    dim3 grid((unsigned)std::max(1, std::min(c->sm_count * 8 / W, 1024)), (unsigned)W);
+    k_pack_blocks<<<grid, 256, 0, s>>>(W, S, U, block_cap[i], dm[i].rp, gathered[i], dm[i].col);
+    c->launches++;
+    ar.release(gathered[i]);
+  }
   CK(cudaGetLastError());
   return CCO_OK;
 }
@@ -442,7 +550,8 @@ static BinCfg make_cfg(cco_ctx *c, int group, int want_slots, int top_k, int n_c
   if (group == 32 && top_k + 32 <= 96) f.cbuf = 128;  // small top_k: a 128-entry buffer doubles the warps per SM (-4 % at C3)
   f.keep_max = std::max(f.final_max, (f.cbuf - group) / 2);
   f.caux = group == 32 ? 0 : f.keep_max;
-  size_t fixed = (size_t)(f.cbuf + f.caux) * 16 + 2 * 256 + 512 + 1024 + (size_t)(group / 32) * 256 + 2048;  // candidates, x12/x11 tables, ctrl, histogram, queues, level-1 cut histogram
+  // candidates, x12/x11 tables, ctrl, radix-select histogram (aliased by the level-1 cut bins), queues
+  size_t fixed = (size_t)(f.cbuf + f.caux) * 16 + 2 * 256 + 512 + 1024 + (size_t)(group / 32) * 256;
   size_t avail = (c->smem_optin - 1024) / groups;  // slack for static shared memory
   int max_slots = (int)((avail - fixed) / 4) & ~1023;
   f.slots = std::min(want_slots, max_slots);
@@ -454,62 +563,62 @@ static BinCfg make_cfg(cco_ctx *c, int group, int want_slots, int top_k, int n_c
   return f;
 }
 
-struct IndicatorOut {
-  int64_t row_begin = 0, row_end = 0;
-  int64_t nnz = 0;
-  int64_t products = 0, distinct = 0, evaluated = 0;
+// ---- one indicator = rows [lo, hi) of A'^T B' on this rank ---------------------------------------------------------------
+// enqueue_indicator puts everything of one indicator on the stream without a single host round trip (the rank partition,
+// the bin bounds and the packed sizes stay on the device); finish_indicator waits for that indicator's mailbox record
+// only -- while the GPU already runs the next indicator -- and starts the device->host copy of its packed arrays.
+struct IndicatorState {
+  int mail_group = -1;
+  long long rec[7] = {0, 0, 0, 0, 0, 0, 0};   // k_indicator_record
+  cudaEvent_t packed = nullptr;                // compaction done (the copy stream waits for it)
+  long long *out_ptr = nullptr;                // [n_items_a + 1], 0 outside the rank's rows
+  int32_t *p_col = nullptr, *p_cnt = nullptr;
+  double *p_llr = nullptr;
+  int32_t n_items_a = 0, n_cols_b = 0;
+  bool emit_all = false;
 };
 
-// One indicator: rows [row_lo,row_hi) of A'^T B'.  Leaves the packed result in pinned host memory.
-static int run_indicator(cco_ctx *c, Arena &ar, const uint32_t *at_ptr, const int32_t *at_users, int32_t n_items_a,
-                         const int32_t *marg_a, int32_t max_marg_a, const DevMat &B, long long n_users, bool self,
-                         const cco_indicator_params_t &prm, uint32_t flags, bool emit_all, int rank, int world,
-                         ResultMat *rm, IndicatorOut *io, float *ms_rows) {
+static int enqueue_indicator(cco_ctx *c, Arena &ar, const uint32_t *at_ptr, const int32_t *at_users, int32_t n_items_a,
+                             const int32_t *marg_a, int32_t max_marg_a, int32_t max_marg_b, const DevMat &B, long long n_users,
+                             bool self, const cco_indicator_params_t &prm, uint32_t flags, bool emit_all, cudaEvent_t ev_begin,
+                             cudaEvent_t ev_end, IndicatorState *st) {
   cudaStream_t s = c->stream;
   const int32_t n_cols_b = B.n_cols;
-  // 1. work per output row + schedule ------------------------------------------------------------
-  uint32_t *row_work, *sorted_work;
+  const int rank = c->rank, world = c->world;
+  st->n_items_a = n_items_a;
+  st->n_cols_b = n_cols_b;
+  st->emit_all = emit_all;
+  // 1. work per output row, rank partition, schedule --------------------------------------------------
+  uint32_t *row_work, *masked, *sorted_work;
   unsigned long long *work64;
   long long *work_prefix;
-  int32_t *ids, *rows_sorted;
+  int32_t *ids, *rows_sorted, *d_pb = nullptr;
   CKR(ar.alloc(&row_work, n_items_a + 1));
+  CKR(ar.alloc(&masked, n_items_a + 1));
   CKR(ar.alloc(&work64, n_items_a + 1));
   CKR(ar.alloc(&work_prefix, n_items_a + 1));
   CKR(ar.alloc(&ids, n_items_a + 1));
+  CKR(ar.alloc(&sorted_work, n_items_a + 1));
+  CKR(ar.alloc(&rows_sorted, n_items_a + 1));
   CK(cudaMemsetAsync(work64 + n_items_a, 0, 8, s));
   k_row_work<<<grid_for((long long)n_items_a * kSG, 256, c->sm_count), 256, 0, s>>>(n_items_a, at_ptr, at_users, B.rp,
-                                                                                 row_work, work64, ids);
+                                                                                 row_work, work64, ids, nullptr);
   c->launches++;
   CKR(exclusive_sum_i64(c, ar, (const long long *)work64, work_prefix, (long long)n_items_a + 1));
-  // rank partition: contiguous item ranges balanced by work prefix (identical on every rank)
-  int32_t row_lo = 0, row_hi = n_items_a;
   if (world > 1) {
-    int32_t *d_pb;
-    std::vector<int32_t> bounds((size_t)world + 1);
+    // contiguous item ranges balanced by work prefix, identical on every rank; they never leave the device
     CKR(ar.alloc(&d_pb, world + 1));
-    k_partition_rows<<<1, 64, 0, s>>>(work_prefix, n_items_a, world, d_pb);   // world <= 63 ranks per job
+    k_partition_rows<<<1, ((world + 1 + 31) / 32) * 32, 0, s>>>(work_prefix, n_items_a, world, d_pb);
     c->launches++;
-    CKR(mail_fetch(c, bounds.data(), d_pb, sizeof(int32_t) * ((size_t)world + 1)));
-    CKR(mail_wait(c));
-    row_lo = bounds[rank];
-    row_hi = bounds[rank + 1];
   }
-  const int32_t n_my = row_hi - row_lo;
-  io->row_begin = row_lo;
-  io->row_end = row_hi;
-  long long hp2[2] = {0, 0};   // filled by the mailbox before the final sync of this indicator
-  CKR(mail_fetch(c, &hp2[0], work_prefix + row_lo, 8));
-  CKR(mail_fetch(c, &hp2[1], work_prefix + row_hi, 8));
-  CKR(ar.alloc(&sorted_work, n_my + 1));
-  CKR(ar.alloc(&rows_sorted, n_my + 1));
-  if (n_my > 0) {
+  k_mask_work<<<grid_for(n_items_a, 256, c->sm_count), 256, 0, s>>>(n_items_a, row_work, d_pb, rank, masked);
+  c->launches++;
+  if (n_items_a > 0) {
     size_t tb = 0;
-    CK(cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, row_work + row_lo, sorted_work, ids + row_lo, rows_sorted,
-                                                 n_my, 0, 32, s));
+    CK(cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, masked, sorted_work, ids, rows_sorted, n_items_a, 0, 32, s));
     void *tmp;
     CKR(ar.alloc((char **)&tmp, tb));
-    CK(cub::DeviceRadixSort::SortPairsDescending(tmp, tb, row_work + row_lo, sorted_work, ids + row_lo, rows_sorted, n_my,
-                                                 0, 32, s));
+    CK(cub::DeviceRadixSort::SortPairsDescending(tmp, tb, masked, sorted_work, ids, rows_sorted, n_items_a, 0, 32, s));
     ar.release(tmp);
   }
   // 2. bins -----------------------------------------------------------------------------------------
@@ -517,13 +626,12 @@ static int run_indicator(cco_ctx *c, Arena &ar, const uint32_t *at_ptr, const in
   const bool warp_ok = k_eff + 32 <= 256;  // warp-owned rows keep a 256-entry candidate buffer
   // Work bins, largest rows first.  {threads that own a row, table words, largest row work w the bin takes}.
   // Bin 0 is the multi-pass bin (same config as bin 1).  Rows up to 1024 products are WARP-owned: no CTA barrier
-  // anywhere in their count / compact / score / select pipeline (profiles/r01_k_rows_ncu_full.md: barriers cost the
-  // CTA-owned bins 35-45 % of their warp time); larger rows need the table and the parallelism of a whole CTA.
+  // anywhere in their count / compact / score / select pipeline; larger rows need the table and the parallelism of a CTA.
   struct BinSpec { int group, slots; uint32_t max_w; };
   std::vector<BinSpec> spec = {{1024, 1 << 20, 0xffffffffu}, {1024, 1 << 20, 0xffffffffu}, {512, 16384, 8192u}, {256, 8192, 4096u}};
   if (warp_ok) {
-    // rows of 1025..2048 products: a 128-thread CTA shares one 4096-word table (9 CTAs/SM) -- a warp-owned 4096-word
-    // table leaves only 10 warps per SM (tools/tune_rows.py: -4 % at C3); up to 1024 products rows are warp-owned
+    // rows of 1025..2048 products: a 128-thread CTA shares one 4096-word table -- a warp-owned 4096-word table leaves
+    // too few warps per SM (tools/tune_rows.py: -4 % at C3); up to 1024 products rows are warp-owned
     spec.push_back({128, 4096, 2048u});
     spec.push_back({32, 2048, 1024u});
     spec.push_back({32, 1024, 512u});
@@ -535,14 +643,18 @@ static int run_indicator(cco_ctx *c, Arena &ar, const uint32_t *at_ptr, const in
   std::vector<BinCfg> cfgs(kBins);
   for (int b = 0; b < kBins; ++b) cfgs[b] = make_cfg(c, spec[b].group, spec[b].slots, k_eff, n_cols_b);
   BinCfg &cfgL = cfgs[1];
-  // packed word: key bits must leave room for the largest possible count (= users of the item)
+  // packed word: key bits must leave room for the largest possible count
   int key_bits = 1;
   while (((1LL << key_bits) - 1) <= (long long)n_cols_b) ++key_bits;  // keys <= 2^kb - 2
   int count_bits = 32 - key_bits;
-  if (count_bits < 1 || (long long)max_marg_a >= (1LL << count_bits))
+  // a co-occurrence count is bounded by both marginals: k11 <= min(rowA, colB) <= min(max rowA, max colB).  With the
+  // reference's default downsampling (m = 500) that is ~560, i.e. 10 count bits next to 22 key bits (4M columns).
+  const long long k11_max = std::min<long long>(max_marg_a, max_marg_b);
+  if (count_bits < 1 || k11_max >= (1LL << count_bits))
     return set_error(CCO_E_UNSUPPORTED,
-                     "an item with %d users and %d columns does not fit the packed 32-bit accumulator word "
-                     "(key %d bits + count %d bits)", max_marg_a, n_cols_b, key_bits, count_bits);
+                     "co-occurrence counts up to %lld over %d columns do not fit the packed 32-bit accumulator word "
+                     "(key %d bits + count %d bits): lower maxItemsPerUser/maxEventsPerEventType for this event type "
+                     "(\"Limits\" in include/cco_b200.h)", k11_max, n_cols_b, key_bits, count_bits);
   // thresholds on w, descending: bin b takes rows with h_thr[b-1] >= w > h_thr[b]; a hashed table also needs w <= cap
   std::vector<uint32_t> h_thr(kBins);
   for (int b = 0; b < kBins; ++b) {
@@ -557,7 +669,7 @@ static int run_indicator(cco_ctx *c, Arena &ar, const uint32_t *at_ptr, const in
   BinThresholds bt;
   memset(&bt, 0, sizeof bt);
   for (int b = 0; b < kBins; ++b) bt.t[b] = h_thr[b];
-  k_bin_bounds<<<1, 32, 0, s>>>(n_my, sorted_work, kBins, bt, d_bounds);
+  k_bin_bounds<<<1, 32, 0, s>>>(n_items_a, sorted_work, kBins, bt, d_bounds);
   c->launches++;
   // per-column constants of B' for the fused LLR
   ColTerm *col_terms;
@@ -591,6 +703,7 @@ static int run_indicator(cco_ctx *c, Arena &ar, const uint32_t *at_ptr, const in
   a.b_col = B.col;
   a.marg_a = marg_a;
   a.marg_b = B.marg;
+  a.max_marg_b = max_marg_b;
   a.col_terms = col_terms;
   a.rows_sorted = rows_sorted;
   a.row_work = row_work;
@@ -612,8 +725,8 @@ static int run_indicator(cco_ctx *c, Arena &ar, const uint32_t *at_ptr, const in
   a.stat_evaluated = d_distinct + 1;
   a.err_flag = d_err;
   a.emit_all = emit_all ? 1 : 0;
-  CK(cudaEventRecord(c->ev[4], s));
-  if (n_my > 0) {
+  if (ev_begin) CK(cudaEventRecord(ev_begin, s));
+  if (n_items_a > 0) {
     // the bins touch disjoint rows: run them concurrently (tails of one bin overlap the bulk of another)
     CK(cudaEventRecord(c->bin_ev[8], s));
     for (int b = 0; b < kBins; ++b) {
@@ -634,65 +747,122 @@ static int run_indicator(cco_ctx *c, Arena &ar, const uint32_t *at_ptr, const in
       CK(cudaStreamWaitEvent(s, c->bin_ev[b], 0));
     }
   }
-  CK(cudaEventRecord(c->ev[5], s));
-  // 4. pack + copy back ---------------------------------------------------------------------------------
-  long long *len64, *out_ptr;
-  CKR(ar.alloc(&len64, n_my + 1));
-  CKR(ar.alloc(&out_ptr, n_my + 1));
-  CK(cudaMemsetAsync(len64 + n_my, 0, 8, s));
-  if (n_my > 0) {
-    k_len_to_i64<<<grid_for(n_my, 256, c->sm_count), 256, 0, s>>>(row_lo, n_my, o_len, len64);
+  if (ev_end) CK(cudaEventRecord(ev_end, s));
+  // 4. pack ---------------------------------------------------------------------------------------------
+  long long *len64, *rec_d;
+  CKR(ar.alloc(&len64, n_items_a + 1));
+  CKR(ar.alloc(&st->out_ptr, n_items_a + 1));
+  CKR(ar.alloc(&rec_d, 8));
+  k_len_to_i64<<<grid_for((long long)n_items_a + 1, 256, c->sm_count), 256, 0, s>>>(n_items_a, o_len, d_pb, rank, len64);
+  c->launches++;
+  CKR(exclusive_sum_i64(c, ar, len64, st->out_ptr, (long long)n_items_a + 1));
+  // the packed size is only known on the device: the buffers take the worst case (every row of the item space full)
+  CKR(ar.alloc(&st->p_col, cells));
+  if (!(flags & CCO_FLAG_RESULT_NO_COUNT) || emit_all) CKR(ar.alloc(&st->p_cnt, cells));
+  if (!emit_all && !(flags & CCO_FLAG_RESULT_NO_LLR)) CKR(ar.alloc(&st->p_llr, cells));
+  if (n_items_a > 0) {
+    k_compact_rows<<<grid_for((long long)n_items_a * 32, 256, c->sm_count), 256, 0, s>>>(n_items_a, stride, st->out_ptr, o_col, o_llr,
+                                                                                      o_cnt, st->p_col, st->p_llr, st->p_cnt);
     c->launches++;
   }
-  CKR(exclusive_sum_i64(c, ar, len64, out_ptr, (long long)n_my + 1));
-  long long total = 0;
-  unsigned long long h_distinct[2] = {0, 0};
-  int h_err = 0;
-  CKR(mail_fetch(c, &total, out_ptr + n_my, 8));
-  CKR(mail_fetch(c, h_distinct, d_distinct, 16));
-  CKR(mail_fetch(c, &h_err, d_err, 4));
-  CKR(mail_wait(c));
-  io->products = hp2[1] - hp2[0];
-  if (h_err) return set_error(CCO_E_CUDA, "internal: shared-memory hash table overflow");
-  io->nnz = total;
-  io->distinct = (int64_t)h_distinct[0];
-  io->evaluated = (int64_t)h_distinct[1];
-  int32_t *p_col, *p_cnt;
-  double *p_llr = nullptr;
-  CKR(ar.alloc(&p_col, std::max<long long>(total, 1)));
-  CKR(ar.alloc(&p_cnt, std::max<long long>(total, 1)));
-  if (!emit_all) CKR(ar.alloc(&p_llr, std::max<long long>(total, 1)));
-  if (n_my > 0 && total > 0) {
-    k_compact_rows<<<grid_for((long long)n_my * 32, 256, c->sm_count), 256, 0, s>>>(row_lo, n_my, stride, out_ptr, o_len,
-                                                                                 o_col, o_llr, o_cnt, p_col, p_llr, p_cnt);
-    c->launches++;
-  }
-  rm->row_begin = row_lo;
-  rm->row_end = row_hi;
-  rm->n_cols = n_cols_b;
-  rm->row_ptr = (int64_t *)c->pinned_get(sizeof(int64_t) * ((size_t)n_my + 1));
-  rm->col = (int32_t *)c->pinned_get(sizeof(int32_t) * (size_t)std::max<long long>(total, 1));
-  rm->cnt = (int32_t *)c->pinned_get(sizeof(int32_t) * (size_t)std::max<long long>(total, 1));
-  rm->llr = (double *)c->pinned_get(sizeof(double) * (size_t)std::max<long long>(total, 1));
-  if (!rm->row_ptr || !rm->col || !rm->cnt || !rm->llr) return set_error(CCO_E_OOM, "pinned host allocation failed");
-  // device -> host on the copy stream so the transfer overlaps the next indicator's kernels; train_dataset joins the
-  // copy stream before it returns (and before the arena frees the packed buffers)
-  cudaStream_t cs = c->copy_stream;
-  CK(cudaEventRecord(c->copy_ev[0], s));
-  CK(cudaStreamWaitEvent(cs, c->copy_ev[0], 0));
-  CK(cudaMemcpyAsync(rm->row_ptr, out_ptr, sizeof(int64_t) * ((size_t)n_my + 1), cudaMemcpyDeviceToHost, cs));
-  if (total > 0 && !(flags & CCO_FLAG_RESULT_ON_DEVICE)) {
-    CK(cudaMemcpyAsync(rm->col, p_col, sizeof(int32_t) * (size_t)total, cudaMemcpyDeviceToHost, cs));
-    CK(cudaMemcpyAsync(rm->cnt, p_cnt, sizeof(int32_t) * (size_t)total, cudaMemcpyDeviceToHost, cs));
-    if (!emit_all) CK(cudaMemcpyAsync(rm->llr, p_llr, sizeof(double) * (size_t)total, cudaMemcpyDeviceToHost, cs));
-  }
-  float ms = 0;
-  CK(cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]));
-  if (ms_rows) *ms_rows = ms;
-  // the strided buffers are dead once k_compact_rows has been enqueued (stream order); the packed ones stay until the
-  // copy stream is joined
-  for (void *p : {(void *)o_col, (void *)o_cnt, (void *)o_llr})
+  k_indicator_record<<<1, 32, 0, s>>>(n_items_a, d_pb, rank, st->out_ptr, work_prefix, d_distinct, d_err, rec_d);
+  c->launches++;
+  CKR(mail_fetch(c, st->rec, rec_d, sizeof(long long) * 7));
+  CKR(mail_close(c, &st->mail_group));
+  if (!st->packed) CK(cudaEventCreateWithFlags(&st->packed, cudaEventDisableTiming));
+  CK(cudaEventRecord(st->packed, s));
+  CK(cudaGetLastError());
+  // the strided buffers are dead once k_compact_rows has been enqueued (stream order)
+  for (void *p : {(void *)o_col, (void *)o_cnt, (void *)o_llr, (void *)len64})
     if (p) ar.release(p);
+  return CCO_OK;
+}
+
+struct IndicatorOut {
+  int64_t row_begin = 0, row_end = 0;
+  int64_t nnz = 0;
+  int64_t products = 0, distinct = 0, evaluated = 0;
+};
+
+// wait for the indicator's record, allocate its host arrays, start the device->host copies on the copy stream
+static int finish_indicator(cco_ctx *c, IndicatorState *st, uint32_t flags, int index, ResultMat *rm, IndicatorOut *io) {
+  CKR(mail_wait_group(c, st->mail_group));
+  const int32_t lo = (int32_t)st->rec[0], hi = (int32_t)st->rec[1];
+  const long long total = st->rec[2];
+  io->row_begin = lo;
+  io->row_end = hi;
+  io->nnz = total;
+  io->products = st->rec[3];
+  io->distinct = st->rec[4];
+  io->evaluated = st->rec[5];
+  if (st->rec[6]) return set_error(CCO_E_CUDA, "internal: shared-memory hash table overflow");
+  const int32_t n_my = hi - lo;
+  cudaStream_t cs = c->copy_stream;
+  CK(cudaStreamWaitEvent(cs, st->packed, 0));
+  GroupShared *gs = c->gshared;
+  int64_t *h_rp;
+  int32_t *h_col, *h_cnt = nullptr;
+  double *h_llr = nullptr;
+  long long base = 0;
+  if (gs) {
+    // group mode: every rank's slice lands in ONE set of host arrays (rank 0 of the group allocates them once all
+    // ranks know their sizes); row pointers are rebased on the device by the cells of the ranks before this one
+    {
+      std::lock_guard<std::mutex> lk(gs->mu);
+      gs->totals[c->rank] = total;
+    }
+    gs->barrier();
+    long long grand = 0;
+    for (int q = 0; q < gs->world; ++q) {
+      if (q < c->rank) base += gs->totals[q];
+      grand += gs->totals[q];
+    }
+    ResultMat &mm = gs->merged->mats[index];
+    if (c->rank == 0) {
+      cco_ctx *owner = gs->merged->ctx;
+      mm.row_begin = 0;
+      mm.row_end = st->n_items_a;
+      mm.n_cols = st->n_cols_b;
+      mm.row_ptr = (int64_t *)owner->pinned_get(sizeof(int64_t) * ((size_t)st->n_items_a + 1));
+      mm.col = (int32_t *)owner->pinned_get(sizeof(int32_t) * (size_t)std::max<long long>(grand, 1));
+      if (st->p_cnt) mm.cnt = (int32_t *)owner->pinned_get(sizeof(int32_t) * (size_t)std::max<long long>(grand, 1));
+      if (st->p_llr) mm.llr = (double *)owner->pinned_get(sizeof(double) * (size_t)std::max<long long>(grand, 1));
+    }
+    gs->barrier();
+    if (!mm.row_ptr || !mm.col || (st->p_cnt && !mm.cnt) || (st->p_llr && !mm.llr)) return set_error(CCO_E_OOM, "pinned host allocation failed");
+    h_rp = mm.row_ptr + lo;
+    h_col = mm.col + base;
+    h_cnt = mm.cnt ? mm.cnt + base : nullptr;
+    h_llr = mm.llr ? mm.llr + base : nullptr;
+    if (base != 0 && n_my >= 0) {
+      k_add_i64<<<grid_for((long long)n_my + 1, 256, c->sm_count, 2), 256, 0, cs>>>((long long)n_my + 1, base, st->out_ptr + lo);
+      c->launches++;
+    }
+    rm->row_begin = lo;   // the member's own record (stats only; the arrays belong to the merged result)
+    rm->row_end = hi;
+    rm->n_cols = st->n_cols_b;
+  } else {
+    rm->row_begin = lo;
+    rm->row_end = hi;
+    rm->n_cols = st->n_cols_b;
+    rm->row_ptr = (int64_t *)c->pinned_get(sizeof(int64_t) * ((size_t)n_my + 1));
+    rm->col = (int32_t *)c->pinned_get(sizeof(int32_t) * (size_t)std::max<long long>(total, 1));
+    if (st->p_cnt) rm->cnt = (int32_t *)c->pinned_get(sizeof(int32_t) * (size_t)std::max<long long>(total, 1));
+    if (st->p_llr) rm->llr = (double *)c->pinned_get(sizeof(double) * (size_t)std::max<long long>(total, 1));
+    if (!rm->row_ptr || !rm->col || (st->p_cnt && !rm->cnt) || (st->p_llr && !rm->llr))
+      return set_error(CCO_E_OOM, "pinned host allocation failed");
+    h_rp = rm->row_ptr;
+    h_col = rm->col;
+    h_cnt = rm->cnt;
+    h_llr = rm->llr;
+  }
+  // out_ptr is 0 up to row lo, so out_ptr[lo .. hi] are the row pointers of this rank's slice relative to its first row
+  CK(cudaMemcpyAsync(h_rp, st->out_ptr + lo, sizeof(int64_t) * ((size_t)n_my + 1), cudaMemcpyDeviceToHost, cs));
+  if (total > 0 && !(flags & CCO_FLAG_RESULT_ON_DEVICE)) {
+    CK(cudaMemcpyAsync(h_col, st->p_col, sizeof(int32_t) * (size_t)total, cudaMemcpyDeviceToHost, cs));
+    if (h_cnt) CK(cudaMemcpyAsync(h_cnt, st->p_cnt, sizeof(int32_t) * (size_t)total, cudaMemcpyDeviceToHost, cs));
+    if (h_llr) CK(cudaMemcpyAsync(h_llr, st->p_llr, sizeof(double) * (size_t)total, cudaMemcpyDeviceToHost, cs));
+  }
   return CCO_OK;
 }
 
@@ -720,19 +890,75 @@ static int validate_host(int32_t n_mats, const cco_csr_t *mats, const cco_indica
   return CCO_OK;
 }
 
-// host CSR -> device (the dataset owns its buffers; they live until cco_dataset_free)
+// the block of user rows rank r of a W-rank job works on
+static inline void user_block(long long U, int W, int r, long long *lo, long long *hi) {
+  const long long S = (U + W - 1) / W;
+  *lo = std::min<long long>((long long)r * S, U);
+  *hi = std::min<long long>(*lo + S, U);
+}
+
 static void dataset_release(cco_dataset *d) {
   if (!d) return;
   cudaSetDevice(d->ctx->device);
-  for (auto p : d->rp)
+  for (auto p : d->rp_alloc)
     if (p) cudaFreeAsync(p, d->ctx->stream);
-  for (auto p : d->col)
+  for (auto p : d->col_alloc)
     if (p) cudaFreeAsync(p, d->ctx->stream);
   for (auto e : d->ready)
     if (e) cudaEventDestroy(e);
   delete d;
 }
 
+// device check of the uploaded block(s) + canonicalisation of unsorted / duplicated rows (synchronous).  In a multi-GPU
+// job the "malformed" verdict is all-reduced so that every rank fails (or proceeds) together.
+static int dataset_validate(cco_ctx *c, cco_dataset *d, bool canonicalise) {
+  cudaStream_t s = c->stream;
+  const int n_mats = d->n_mats;
+  Arena ar(s);
+  int *d_flags;
+  CKR(ar.alloc(&d_flags, 2 * n_mats));
+  CK(cudaMemsetAsync(d_flags, 0, sizeof(int) * 2 * n_mats, s));
+  for (int i = 0; i < n_mats; ++i) {
+    CK(cudaStreamWaitEvent(s, d->ready[i], 0));
+    if (d->n_local == 0) continue;
+    k_check_rows<<<grid_for(d->n_local * kSG, 256, c->sm_count), 256, 0, s>>>(d->n_local, (int32_t)d->n_cols[i], d->rp[i], d->col[i],
+                                                                          d_flags + 2 * i);
+    c->launches++;
+  }
+  if (c->world > 1)
+    CKR(nccl_check(g_nccl.AllReduce(d_flags, d_flags, (size_t)(2 * n_mats), kNcclInt32, kNcclMax, c->comm, s), "ncclAllReduce(check flags)"));
+  std::vector<int> h(2 * n_mats);
+  CK(cudaMemcpyAsync(h.data(), d_flags, sizeof(int) * 2 * n_mats, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  CK(cudaGetLastError());
+  for (int i = 0; i < n_mats; ++i)
+    if (h[2 * i]) return set_error(CCO_E_INVALID_ARG, "matrix %d: row_ptr not monotone or column index out of [0, n_cols)", i);
+  if (canonicalise)
+    for (int i = 0; i < n_mats; ++i)
+      if (h[2 * i + 1] && d->n_local > 0) {
+        // (the flag is all-reduced: every rank canonicalises its own block, the blocks are independent)
+        DevRaw r;
+        r.n_rows = d->n_local;
+        r.row_base = d->row_base;
+        r.n_cols = (int32_t)d->n_cols[i];
+        long long q0 = 0, q1 = 0;
+        CK(cudaMemcpyAsync(&q0, d->rp[i], 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(&q1, d->rp[i] + d->n_local, 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        r.q_base = q0;
+        r.nnz = q1 - q0;
+        r.rp = d->rp[i];
+        r.col = d->col[i];
+        CKR(canonicalize_device(c, ar, r));
+        d->col[i] = r.col;
+        if (c->world == 1) d->nnz[i] = r.nnz;
+      }
+  CK(cudaStreamSynchronize(s));
+  d->validated = canonicalise;
+  return CCO_OK;
+}
+
+// host CSR -> device: this rank's block of user rows only (the dataset owns its buffers until cco_dataset_free)
 static int dataset_upload(cco_ctx *c, int32_t n_mats, const cco_csr_t *mats, uint32_t flags, cco_dataset **out, bool async = false) {
   CK(cudaSetDevice(c->device));
   cudaStream_t s = c->stream;
@@ -740,10 +966,18 @@ static int dataset_upload(cco_ctx *c, int32_t n_mats, const cco_csr_t *mats, uin
   d->ctx = c;
   d->n_mats = n_mats;
   d->n_users = mats[0].n_rows;
+  long long u_lo, u_hi;
+  user_block(d->n_users, c->world, c->rank, &u_lo, &u_hi);
+  d->row_base = u_lo;
+  d->n_local = u_hi - u_lo;
+  d->whole = c->world == 1;
   d->rp.assign(n_mats, nullptr);
   d->col.assign(n_mats, nullptr);
+  d->rp_alloc.assign(n_mats, nullptr);
+  d->col_alloc.assign(n_mats, nullptr);
   d->n_cols.assign(n_mats, 0);
   d->nnz.assign(n_mats, 0);
+  d->block_cap.assign(n_mats, 0);
   d->ready.assign(n_mats, nullptr);
   struct G {
     cco_dataset *d;
@@ -759,13 +993,21 @@ static int dataset_upload(cco_ctx *c, int32_t n_mats, const cco_csr_t *mats, uin
     const cco_csr_t &m = mats[i];
     d->n_cols[i] = m.n_cols;
     d->nnz[i] = m.row_ptr[m.n_rows];
+    for (int q = 0; q < c->world; ++q) {
+      long long a0, a1;
+      user_block(d->n_users, c->world, q, &a0, &a1);
+      d->block_cap[i] = std::max<long long>(d->block_cap[i], m.row_ptr[a1] - m.row_ptr[a0]);
+    }
+    const long long q0 = m.row_ptr[u_lo], q1 = m.row_ptr[u_hi];
     void *p = nullptr;
-    cudaError_t e = cudaMallocAsync(&p, sizeof(int64_t) * ((size_t)m.n_rows + 1), s);
+    cudaError_t e = cudaMallocAsync(&p, sizeof(int64_t) * ((size_t)d->n_local + 1), s);
     if (e != cudaSuccess) return set_error(CCO_E_OOM, "cudaMallocAsync row_ptr: %s", cudaGetErrorString(e));
+    d->rp_alloc[i] = p;
     d->rp[i] = (long long *)p;
-    e = cudaMallocAsync(&p, sizeof(int32_t) * (size_t)std::max<long long>(d->nnz[i], 4), s);
+    e = cudaMallocAsync(&p, sizeof(int32_t) * (size_t)std::max<long long>(q1 - q0, 4), s);
     if (e != cudaSuccess) return set_error(CCO_E_OOM, "cudaMallocAsync col_idx: %s", cudaGetErrorString(e));
-    d->col[i] = (int32_t *)p;
+    d->col_alloc[i] = p;
+    d->col[i] = (int32_t *)p - q0;   // the block keeps the caller's absolute offsets: col[rp[r]] addresses its own storage
     CK(cudaEventCreateWithFlags(&d->ready[i], cudaEventDisableTiming));
   }
   CK(cudaEventRecord(c->copy_ev[0], s));
@@ -773,62 +1015,33 @@ static int dataset_upload(cco_ctx *c, int32_t n_mats, const cco_csr_t *mats, uin
   CK(cudaEventRecord(c->ev[6], cs));
   for (int i = 0; i < n_mats; ++i) {
     const cco_csr_t &m = mats[i];
-    CK(cudaMemcpyAsync(d->rp[i], m.row_ptr, sizeof(int64_t) * ((size_t)m.n_rows + 1), cudaMemcpyHostToDevice, cs));
-    if (d->nnz[i] > 0)
-      CK(cudaMemcpyAsync(d->col[i], m.col_idx, sizeof(int32_t) * (size_t)d->nnz[i], cudaMemcpyHostToDevice, cs));
+    const long long q0 = m.row_ptr[u_lo], q1 = m.row_ptr[u_hi];
+    CK(cudaMemcpyAsync(d->rp_alloc[i], m.row_ptr + u_lo, sizeof(int64_t) * ((size_t)d->n_local + 1), cudaMemcpyHostToDevice, cs));
+    if (q1 > q0)
+      CK(cudaMemcpyAsync(d->col_alloc[i], m.col_idx + q0, sizeof(int32_t) * (size_t)(q1 - q0), cudaMemcpyHostToDevice, cs));
     CK(cudaEventRecord(d->ready[i], cs));
   }
   CK(cudaEventRecord(c->ev[7], cs));
   if (async && (flags & CCO_FLAG_ASSUME_CANONICAL)) {
-    d->h2d_pending = true;
+    d->h2d_pending = true;   // the malformed-input check runs inside the train, next to the first pass over the data
     g.ok = true;
     *out = d;
     return CCO_OK;
   }
-  for (int i = 0; i < n_mats; ++i) CK(cudaStreamWaitEvent(s, d->ready[i], 0));
-  // check + (if needed) canonicalise in place
-  if (!(flags & CCO_FLAG_ASSUME_CANONICAL)) {
-    Arena ar(s);
-    int *d_flags;
-    CKR(ar.alloc(&d_flags, 2 * n_mats));
-    CK(cudaMemsetAsync(d_flags, 0, sizeof(int) * 2 * n_mats, s));
-    for (int i = 0; i < n_mats; ++i) {
-      k_check_rows<<<grid_for(d->n_users * kSG, 256, c->sm_count), 256, 0, s>>>(d->n_users, (int32_t)d->n_cols[i], d->rp[i],
-                                                                             d->col[i], d_flags + 2 * i);
-      c->launches++;
-    }
-    std::vector<int> h(2 * n_mats);
-    CK(cudaMemcpyAsync(h.data(), d_flags, sizeof(int) * 2 * n_mats, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    CK(cudaGetLastError());
-    for (int i = 0; i < n_mats; ++i)
-      if (h[2 * i]) return set_error(CCO_E_INVALID_ARG, "matrix %d: row_ptr not monotone or column index out of [0, n_cols)", i);
-    for (int i = 0; i < n_mats; ++i)
-      if (h[2 * i + 1]) {
-        DevRaw r;
-        r.n_rows = d->n_users;
-        r.n_cols = (int32_t)d->n_cols[i];
-        r.nnz = d->nnz[i];
-        r.rp = d->rp[i];
-        r.col = d->col[i];
-        CKR(canonicalize_device(c, ar, r));
-        d->nnz[i] = r.nnz;
-      }
-  }
-  CK(cudaStreamSynchronize(s));
+  CKR(dataset_validate(c, d, !(flags & CCO_FLAG_ASSUME_CANONICAL)));
   CK(cudaEventElapsedTime(&d->ms_h2d, c->ev[6], c->ev[7]));
   g.ok = true;
   *out = d;
   return CCO_OK;
 }
 
+// The whole hot path on this rank, for the block of users the dataset holds.
 static int train_dataset(cco_ctx *c, const cco_dataset *ds, const cco_indicator_params_t *params, int32_t seed, uint32_t flags,
                          cco_result **out) {
   CK(cudaSetDevice(c->device));
   cudaStream_t s = c->stream;
   const int n_mats = ds->n_mats;
-  c->mail_pending.clear();
-  c->mail_used = 0;
+  mail_reset(c);
   Arena ar(s);
   struct CopyJoin {  // destroyed before `ar`: no packed buffer is freed while the copy stream still reads it
     cco_ctx *c;
@@ -845,6 +1058,16 @@ static int train_dataset(cco_ctx *c, const cco_dataset *ds, const cco_indicator_
       if (!ok) cco_result_free(r);
     }
   } guard{res};
+  std::vector<IndicatorState> ist(n_mats);
+  struct EvGuard {
+    std::vector<IndicatorState> &v;
+    std::vector<cudaEvent_t> extra;
+    ~EvGuard() {
+      for (auto &x : v)
+        if (x.packed) cudaEventDestroy(x.packed);
+      for (auto e : extra) cudaEventDestroy(e);
+    }
+  } evg{ist, {}};
   cco_stats_t &st = res->stats;
   st.n_mats = n_mats;
   st.n_users = ds->n_users;
@@ -853,15 +1076,18 @@ static int train_dataset(cco_ctx *c, const cco_dataset *ds, const cco_indicator_
   const long long n_users = ds->n_users;
   std::vector<DevRaw> raw(n_mats);
   for (int i = 0; i < n_mats; ++i) {
-    raw[i].n_rows = n_users;
+    raw[i].n_rows = ds->n_local;
+    raw[i].row_base = ds->row_base;
     raw[i].n_cols = (int32_t)ds->n_cols[i];
-    raw[i].nnz = ds->nnz[i];
+    raw[i].nnz = ds->nnz[i];   // bound: the block never holds more than the whole matrix
+    raw[i].nnz_cap = ds->nnz[i];
     raw[i].rp = ds->rp[i];
     raw[i].col = ds->col[i];
-    st.nnz_in_total += raw[i].nnz;
+    st.nnz_in_total += ds->nnz[i];
   }
   CK(cudaEventRecord(c->ev[1], s));
-  // raw column counts: this rank histograms its user slice; ONE allreduce sums all matrices' counts
+  nvtx_push("cco:prepare");
+  // raw column counts: this rank histograms its user block; ONE allreduce sums all matrices' counts
   long long total_cols = 0;
   std::vector<long long> col_off(n_mats + 1, 0);
   for (int i = 0; i < n_mats; ++i) {
@@ -871,14 +1097,24 @@ static int train_dataset(cco_ctx *c, const cco_dataset *ds, const cco_indicator_
   col_off[n_mats] = total_cols;
   constexpr int kHistCopies = 16;
   const long long copy_stride = std::max<long long>(total_cols, 1);
-  int32_t *raw_counts;
+  int32_t *raw_counts, *marg_all;
+  int *d_check;
   CKR(ar.alloc(&raw_counts, (size_t)copy_stride * kHistCopies));
+  CKR(ar.alloc(&marg_all, (size_t)copy_stride));
+  CKR(ar.alloc(&d_check, 2 * n_mats));
   CK(cudaMemsetAsync(raw_counts, 0, sizeof(int32_t) * (size_t)copy_stride * kHistCopies, s));
-  const long long u_lo = n_users * c->rank / c->world, u_hi = n_users * (c->rank + 1) / c->world;
+  CK(cudaMemsetAsync(marg_all, 0, sizeof(int32_t) * (size_t)copy_stride, s));
+  CK(cudaMemsetAsync(d_check, 0, sizeof(int) * 2 * n_mats, s));
   for (int i = 0; i < n_mats; ++i) {
     CK(cudaStreamWaitEvent(s, ds->ready[i], 0));  // matrix i has landed (async upload: later ones may still be in flight)
-    if (raw[i].nnz == 0 || u_hi == u_lo) continue;
-    k_col_histogram<<<grid_for(raw[i].nnz / c->world + 1, 256, c->sm_count), 256, 0, s>>>(u_lo, u_hi, raw[i].rp, raw[i].col,
+    if (ds->n_local == 0) continue;
+    if (!ds->validated) {
+      // CCO_FLAG_ASSUME_CANONICAL skips the canonicalisation, not the safety net: a malformed matrix still fails the call
+      k_check_rows<<<grid_for(ds->n_local * kSG, 256, c->sm_count), 256, 0, s>>>(ds->n_local, raw[i].n_cols, raw[i].rp, raw[i].col,
+                                                                             d_check + 2 * i);
+      c->launches++;
+    }
+    k_col_histogram<<<grid_for(raw[i].nnz / c->world + 1, 256, c->sm_count), 256, 0, s>>>(0, ds->n_local, raw[i].rp, raw[i].col,
                                                                                        raw_counts + col_off[i], kHistCopies, copy_stride);
     c->launches++;
   }
@@ -887,16 +1123,19 @@ static int train_dataset(cco_ctx *c, const cco_dataset *ds, const cco_indicator_
     c->launches++;
   }
   if (c->world > 1) {
-    int r = g_nccl.AllReduce(raw_counts, raw_counts, (size_t)total_cols, kNcclInt32, kNcclSum, c->comm, s);
-    if (r != 0) return set_error(CCO_E_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString(r));
+    if (total_cols > 0)
+      CKR(nccl_check(g_nccl.AllReduce(raw_counts, raw_counts, (size_t)total_cols, kNcclInt32, kNcclSum, c->comm, s), "ncclAllReduce(raw counts)"));
+    CKR(nccl_check(g_nccl.AllReduce(d_check, d_check, (size_t)(2 * n_mats), kNcclInt32, kNcclMax, c->comm, s), "ncclAllReduce(check flags)"));
   }
   // sampleDownAndBinarize every matrix
   std::vector<DevMat> dm(n_mats);
   if (c->world > 1) {
-    CKR(downsample_sharded_all(c, ar, raw, raw_counts, col_off, params, seed, flags, dm));
+    CKR(downsample_sharded_all(c, ar, raw, ds->block_cap, n_users, raw_counts, marg_all, col_off, params, seed, flags, dm));
   } else {
-    for (int i = 0; i < n_mats; ++i)
+    for (int i = 0; i < n_mats; ++i) {
+      dm[i].marg = marg_all + col_off[i];
       CKR(downsample_device(c, ar, raw[i], raw_counts + col_off[i], params[i].max_interactions, seed, flags, &dm[i]));
+    }
   }
   // `drmA.t`
   const int32_t n_items_a = dm[0].n_cols;
@@ -904,9 +1143,9 @@ static int train_dataset(cco_ctx *c, const cco_dataset *ds, const cco_indicator_
   int32_t *at_users, *d_max;
   CKR(ar.alloc(&at_ptr, n_items_a + 1));
   CKR(ar.alloc(&cursor, n_items_a + 1));
-  CKR(ar.alloc(&d_max, 1));
-  CKR(ar.alloc(&at_users, std::max<long long>(raw[0].nnz, 1)));
-  CK(cudaMemsetAsync(d_max, 0, 4, s));
+  CKR(ar.alloc(&d_max, n_mats));
+  CKR(ar.alloc(&at_users, std::max<long long>(ds->nnz[0], 1)));
+  CK(cudaMemsetAsync(d_max, 0, 4 * (size_t)n_mats, s));
   {
     uint32_t *marg_pad;
     CKR(ar.alloc(&marg_pad, n_items_a + 1));
@@ -918,36 +1157,51 @@ static int train_dataset(cco_ctx *c, const cco_dataset *ds, const cco_indicator_
   CK(cudaMemcpyAsync(cursor, at_ptr, sizeof(uint32_t) * ((size_t)n_items_a + 1), cudaMemcpyDeviceToDevice, s));
   k_transpose_scatter<<<grid_for(n_users * kSG, 256, c->sm_count), 256, 0, s>>>(n_users, dm[0].rp, dm[0].col, cursor, at_users);
   c->launches++;
-  if (n_items_a > 0) {
-    k_max_i32<<<grid_for(n_items_a, 256, c->sm_count, 2), 256, 0, s>>>(n_items_a, dm[0].marg, d_max);
-    c->launches++;
-  }
-  int32_t max_marg_a = 0;
+  for (int i = 0; i < n_mats; ++i)
+    if (dm[i].n_cols > 0) {
+      k_max_i32<<<grid_for(dm[i].n_cols, 256, c->sm_count, 2), 256, 0, s>>>(dm[i].n_cols, dm[i].marg, d_max + i);
+      c->launches++;
+    }
+  std::vector<int32_t> max_marg(n_mats, 0);
   std::vector<uint32_t> h_nnz(n_mats);
-  CKR(mail_fetch(c, &max_marg_a, d_max, 4));
+  std::vector<int> h_check(2 * n_mats, 0);
+  CKR(mail_fetch(c, max_marg.data(), d_max, 4 * (size_t)n_mats));
+  CKR(mail_fetch(c, h_check.data(), d_check, sizeof(int) * 2 * (size_t)n_mats));
   for (int i = 0; i < n_mats; ++i) CKR(mail_fetch(c, &h_nnz[i], dm[i].rp + n_users, 4));
   CK(cudaEventRecord(c->ev[2], s));
-  CKR(mail_wait(c));
+  nvtx_pop();
+  CKR(mail_wait(c));   // the one host round trip of the preparation: the packed-word check needs the largest marginals
+  for (int i = 0; i < n_mats; ++i)
+    if (h_check[2 * i]) return set_error(CCO_E_INVALID_ARG, "matrix %d: row_ptr not monotone or column index out of [0, n_cols)", i);
   for (int i = 0; i < n_mats && i < 16; ++i) st.nnz_downsampled[i] = h_nnz[i];
 
-  for (int i = 0; i < n_mats; ++i) {
-    IndicatorOut io;
-    float ms_rows = 0;
-    CKR(run_indicator(c, ar, at_ptr, at_users, n_items_a, dm[0].marg, max_marg_a, dm[i], n_users, i == 0, params[i], flags,
-                      false, c->rank, c->world, &res->mats[i], &io, &ms_rows));
-    if (i < 16) {
-      st.products[i] = io.products;
-      st.distinct_cells[i] = io.distinct;
-      st.llr_evaluated[i] = io.evaluated;
-      st.out_nnz[i] = io.nnz;
-      st.ms_indicator[i] = ms_rows;
-    }
+  // indicators, software-pipelined: indicator i+1 is on the stream before the host waits for indicator i's record
+  std::vector<IndicatorOut> io(n_mats);
+  std::vector<cudaEvent_t> ev_rows(2 * n_mats, nullptr);
+  for (auto &e : ev_rows) {
+    CK(cudaEventCreate(&e));
+    evg.extra.push_back(e);
   }
+  for (int i = 0; i < n_mats; ++i) {
+    nvtx_push("cco:indicator");
+    CKR(enqueue_indicator(c, ar, at_ptr, at_users, n_items_a, dm[0].marg, max_marg[0], max_marg[i], dm[i], n_users, i == 0, params[i],
+                          flags, false, ev_rows[2 * i], ev_rows[2 * i + 1], &ist[i]));
+    nvtx_pop();
+    if (i > 0) CKR(finish_indicator(c, &ist[i - 1], flags, i - 1, &res->mats[i - 1], &io[i - 1]));
+  }
+  CKR(finish_indicator(c, &ist[n_mats - 1], flags, n_mats - 1, &res->mats[n_mats - 1], &io[n_mats - 1]));
   CK(cudaEventRecord(c->copy_ev[1], c->copy_stream));
   CK(cudaStreamWaitEvent(s, c->copy_ev[1], 0));
   CK(cudaEventRecord(c->ev[3], s));
   CK(cudaStreamSynchronize(s));
   CK(cudaStreamSynchronize(c->copy_stream));
+  for (int i = 0; i < n_mats && i < 16; ++i) {
+    st.products[i] = io[i].products;
+    st.distinct_cells[i] = io[i].distinct;
+    st.llr_evaluated[i] = io[i].evaluated;
+    st.out_nnz[i] = io[i].nnz;
+    CK(cudaEventElapsedTime(&st.ms_indicator[i], ev_rows[2 * i], ev_rows[2 * i + 1]));
+  }
   if (h2d_pending) CK(cudaEventElapsedTime(&st.ms_h2d, c->ev[6], c->ev[7]));
   CK(cudaEventElapsedTime(&st.ms_prepare, c->ev[1], c->ev[2]));
   CK(cudaEventElapsedTime(&st.ms_cooccurrence, c->ev[2], c->ev[3]));
@@ -961,7 +1215,6 @@ static int train_dataset(cco_ctx *c, const cco_dataset *ds, const cco_indicator_
 
 static int train_impl(cco_ctx *c, int32_t n_mats, const cco_csr_t *mats, const cco_indicator_params_t *params, int32_t seed,
                       uint32_t flags, cco_result **out) {
-  CKR(validate_host(n_mats, mats, params));
   c->launches = 0;
   cco_dataset *ds = nullptr;
   CKR(dataset_upload(c, n_mats, mats, flags, &ds, /*async=*/true));
@@ -969,6 +1222,63 @@ static int train_impl(cco_ctx *c, int32_t n_mats, const cco_csr_t *mats, const c
   cudaStreamSynchronize(c->copy_stream);  // the caller's host buffers are free again when cco_train returns
   dataset_release(ds);
   return rc;
+}
+
+// cco_train on a group context: one host thread per GPU runs the per-rank train on its member context (same host
+// matrices, each thread uploads its block of users); the slices meet in one merged result owned by the leader.
+static int train_group(cco_ctx *leader, int32_t n_mats, const cco_csr_t *mats, const cco_indicator_params_t *params, int32_t seed,
+                       uint32_t flags, cco_result **out) {
+  const int W = (int)leader->members.size();
+  GroupShared *gs = leader->members[0]->gshared;
+  cco_result *merged = new cco_result();
+  merged->ctx = leader;
+  merged->mats.resize(n_mats);
+  memset(&merged->stats, 0, sizeof merged->stats);
+  gs->merged = merged;
+  gs->totals.assign(W, 0);
+  gs->status = CCO_OK;
+  gs->err[0] = 0;
+  std::vector<cco_result *> part(W, nullptr);
+  std::vector<std::thread> th;
+  for (int r = 0; r < W; ++r)
+    th.emplace_back([&, r]() {
+      int rc = train_impl(leader->members[r], n_mats, mats, params, seed, flags, &part[r]);
+      if (rc != CCO_OK) {
+        std::lock_guard<std::mutex> lk(gs->mu);
+        if (gs->status == CCO_OK) {
+          gs->status = rc;
+          snprintf(gs->err, sizeof gs->err, "GPU %d: %s", leader->members[r]->device, cco_last_error());
+        }
+      }
+    });
+  for (auto &t : th) t.join();
+  gs->merged = nullptr;
+  if (gs->status != CCO_OK) {
+    for (auto p : part)
+      if (p) cco_result_free(p);
+    cco_result_free(merged);
+    return set_error(gs->status, "%s", gs->err);
+  }
+  cco_stats_t &st = merged->stats;
+  st = part[0]->stats;
+  for (int r = 1; r < W; ++r) {
+    const cco_stats_t &p = part[r]->stats;
+    for (int i = 0; i < 16; ++i) {
+      st.products[i] += p.products[i];
+      st.distinct_cells[i] += p.distinct_cells[i];
+      st.out_nnz[i] += p.out_nnz[i];
+      st.llr_evaluated[i] += p.llr_evaluated[i];
+      st.ms_indicator[i] = std::max(st.ms_indicator[i], p.ms_indicator[i]);
+    }
+    st.ms_h2d = std::max(st.ms_h2d, p.ms_h2d);
+    st.ms_prepare = std::max(st.ms_prepare, p.ms_prepare);
+    st.ms_cooccurrence = std::max(st.ms_cooccurrence, p.ms_cooccurrence);
+    st.ms_total = std::max(st.ms_total, p.ms_total);
+    st.n_kernel_launches += p.n_kernel_launches;
+  }
+  for (auto p : part) cco_result_free(p);
+  *out = merged;
+  return CCO_OK;
 }
 
 }  // namespace cco
@@ -1142,15 +1452,16 @@ int cco_dataset_shape(const cco_dataset_t *ds, int32_t i, int64_t *n_rows, int32
 
 int cco_dataset_download(const cco_dataset_t *ds, int32_t i, int64_t **row_ptr, int32_t **col_idx) {
   if (!ds || !row_ptr || !col_idx || i < 0 || i >= ds->n_mats) return set_error(CCO_E_INVALID_ARG, "bad argument");
+  if (!ds->whole) return set_error(CCO_E_UNSUPPORTED, "this dataset holds one rank's block of users only");
   cco_ctx *c = ds->ctx;
   CK(cudaSetDevice(c->device));
   int64_t *rp = (int64_t *)malloc(sizeof(int64_t) * ((size_t)ds->n_users + 1));
   int32_t *ci = (int32_t *)malloc(sizeof(int32_t) * (size_t)std::max<long long>(ds->nnz[i], 1));
   if (!rp || !ci) return set_error(CCO_E_OOM, "malloc failed");
   CK(cudaStreamSynchronize(c->copy_stream));
-  CK(cudaMemcpyAsync(rp, ds->rp[i], sizeof(int64_t) * ((size_t)ds->n_users + 1), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(rp, ds->rp_alloc[i], sizeof(int64_t) * ((size_t)ds->n_users + 1), cudaMemcpyDeviceToHost, c->stream));
   if (ds->nnz[i] > 0)
-    CK(cudaMemcpyAsync(ci, ds->col[i], sizeof(int32_t) * (size_t)ds->nnz[i], cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(ci, ds->col_alloc[i], sizeof(int32_t) * (size_t)ds->nnz[i], cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   *row_ptr = rp;
   *col_idx = ci;
@@ -1158,35 +1469,40 @@ int cco_dataset_download(const cco_dataset_t *ds, int32_t i, int64_t **row_ptr, 
 }
 
 // Preparator.prepare on the device: histogram + scans for the dictionaries, one radix sort + unique
-// per event type for the binary CSR.
-int cco_ingest(cco_ctx_t *c, int32_t n_types, const cco_events_t *ev, int64_t n_users_raw, int32_t min_events_per_user,
-               int32_t *user_map, int32_t *const *item_maps, cco_dataset_t **out) {
-  if (!c || !ev || !user_map || !item_maps || !out || n_types < 1) return set_error(CCO_E_INVALID_ARG, "bad argument");
-  if (n_users_raw < 0 || n_users_raw >= 0x7fffffffLL) return set_error(CCO_E_INVALID_ARG, "n_users_raw out of range");
-  for (int t = 0; t < n_types; ++t) {
-    if (ev[t].n_events < 0 || ev[t].n_events >= 0xffffffffLL || ev[t].n_items_raw < 0)
-      return set_error(CCO_E_INVALID_ARG, "type %d: bad event count / item space", t);
-    if (ev[t].n_events > 0 && (!ev[t].user || !ev[t].item)) return set_error(CCO_E_INVALID_ARG, "type %d: null event arrays", t);
-    if (!item_maps[t] && ev[t].n_items_raw > 0) return set_error(CCO_E_INVALID_ARG, "type %d: null item_map", t);
-    // ids are range-checked on the host: they index device arrays
-    for (int64_t i = 0; i < ev[t].n_events; ++i)
-      if (ev[t].user[i] < 0 || ev[t].user[i] >= n_users_raw || ev[t].item[i] < 0 || ev[t].item[i] >= ev[t].n_items_raw)
-        return set_error(CCO_E_INVALID_ARG, "type %d: user or item id out of range at event %lld", t, (long long)i);
-  }
+// per event type for the binary CSR.  The events of a type reach the device through `fill` (a host->device copy for
+// cco_ingest, the generator kernel for cco_synth_ingest) right before the type is processed.
+struct IngestSource {
+  int n_types = 0;
+  long long n_users_raw = 0;
+  std::vector<long long> n_events;
+  std::vector<int32_t> n_items_raw;
+  bool keep_item_space = false;   // synthetic workloads: the item dictionary is the raw id space (identity map)
+  // fill(t, d_user, d_item): enqueue on the context's stream whatever puts type t's raw events into the two arrays
+  std::function<int(int, long long *, int32_t *)> fill;
+};
+
+static int ingest_core(cco_ctx *c, const IngestSource &src, int32_t min_events_per_user, int32_t *user_map,
+                       int32_t *const *item_maps, cco_dataset **out) {
+  const int n_types = src.n_types;
+  const long long n_users_raw = src.n_users_raw;
   *out = nullptr;
   CK(cudaSetDevice(c->device));
   cudaStream_t s = c->stream;
-  c->mail_pending.clear();
-  c->mail_used = 0;
+  mail_reset(c);
   Arena ar(s);
   cco_dataset *d = new cco_dataset();
   d->ctx = c;
   d->n_mats = n_types;
   d->rp.assign(n_types, nullptr);
   d->col.assign(n_types, nullptr);
+  d->rp_alloc.assign(n_types, nullptr);
+  d->col_alloc.assign(n_types, nullptr);
+  d->block_cap.assign(n_types, 0);
   d->n_cols.assign(n_types, 0);
   d->nnz.assign(n_types, 0);
   d->ready.assign(n_types, nullptr);
+  d->validated = true;   // built here: canonical by construction
+  d->whole = true;
   struct G {
     cco_dataset *d;
     bool ok = false;
@@ -1195,82 +1511,87 @@ int cco_ingest(cco_ctx_t *c, int32_t n_types, const cco_events_t *ev, int64_t n_
     }
   } g{d};
   const long long nu = std::max<long long>(n_users_raw, 1);
-  // events to the device
-  std::vector<long long *> d_user(n_types, nullptr);
-  std::vector<int32_t *> d_item(n_types, nullptr);
-  for (int t = 0; t < n_types; ++t) {
-    CKR(ar.alloc(&d_user[t], std::max<long long>(ev[t].n_events, 1)));
-    CKR(ar.alloc(&d_item[t], std::max<long long>(ev[t].n_events, 1)));
-    if (ev[t].n_events > 0) {
-      CK(cudaMemcpyAsync(d_user[t], ev[t].user, sizeof(int64_t) * (size_t)ev[t].n_events, cudaMemcpyHostToDevice, s));
-      CK(cudaMemcpyAsync(d_item[t], ev[t].item, sizeof(int32_t) * (size_t)ev[t].n_events, cudaMemcpyHostToDevice, s));
-    }
-  }
-  // user dictionary from the primary events
   int32_t *cnt, *d_user_map;
   uint32_t *uflag, *upos;
   CKR(ar.alloc(&cnt, nu));
   CKR(ar.alloc(&uflag, nu + 1));
   CKR(ar.alloc(&upos, nu + 1));
   CKR(ar.alloc(&d_user_map, nu));
-  CK(cudaMemsetAsync(cnt, 0, sizeof(int32_t) * (size_t)nu, s));
-  CK(cudaMemsetAsync(uflag, 0, sizeof(uint32_t) * ((size_t)nu + 1), s));
-  if (ev[0].n_events > 0)
-    k_ingest_count_users<<<grid_for(ev[0].n_events, 256, c->sm_count), 256, 0, s>>>(ev[0].n_events, d_user[0], cnt);
-  const int32_t need = min_events_per_user > 1 ? min_events_per_user : 1;
-  if (n_users_raw > 0)
-    k_ingest_user_flags<<<grid_for(n_users_raw, 256, c->sm_count), 256, 0, s>>>(n_users_raw, cnt, need, uflag);
-  CKR(exclusive_sum_u32(c, ar, uflag, upos, nu + 1));
-  if (n_users_raw > 0)
-    k_ingest_make_map<<<grid_for(n_users_raw, 256, c->sm_count), 256, 0, s>>>(n_users_raw, uflag, upos, d_user_map);
-  c->launches += 3;
   uint32_t n_users = 0;
-  CKR(mail_fetch(c, &n_users, upos + n_users_raw, 4));
-  if (n_users_raw > 0)
-    CK(cudaMemcpyAsync(user_map, d_user_map, sizeof(int32_t) * (size_t)n_users_raw, cudaMemcpyDeviceToHost, s));
-  CKR(mail_wait(c));
-  d->n_users = n_users;
   for (int t = 0; t < n_types; ++t) {
-    const long long ne = ev[t].n_events, ni = std::max<int32_t>(ev[t].n_items_raw, 1);
+    const long long ne = src.n_events[t], ni = std::max<int32_t>(src.n_items_raw[t], 1);
+    long long *d_user;
+    int32_t *d_item;
+    CKR(ar.alloc(&d_user, std::max<long long>(ne, 1)));
+    CKR(ar.alloc(&d_item, std::max<long long>(ne, 1)));
+    if (ne > 0) CKR(src.fill(t, d_user, d_item));
+    if (t == 0) {
+      // user dictionary from the primary events (duplicates count: Preparator.scala:129-132)
+      CK(cudaMemsetAsync(cnt, 0, sizeof(int32_t) * (size_t)nu, s));
+      CK(cudaMemsetAsync(uflag, 0, sizeof(uint32_t) * ((size_t)nu + 1), s));
+      if (ne > 0) k_ingest_count_users<<<grid_for(ne, 256, c->sm_count), 256, 0, s>>>(ne, d_user, cnt);
+      const int32_t need = min_events_per_user > 1 ? min_events_per_user : 1;
+      if (n_users_raw > 0)
+        k_ingest_user_flags<<<grid_for(n_users_raw, 256, c->sm_count), 256, 0, s>>>(n_users_raw, cnt, need, uflag);
+      CKR(exclusive_sum_u32(c, ar, uflag, upos, nu + 1));
+      if (n_users_raw > 0)
+        k_ingest_make_map<<<grid_for(n_users_raw, 256, c->sm_count), 256, 0, s>>>(n_users_raw, uflag, upos, d_user_map);
+      c->launches += 3;
+      CKR(mail_fetch(c, &n_users, upos + n_users_raw, 4));
+      if (n_users_raw > 0 && user_map)
+        CK(cudaMemcpyAsync(user_map, d_user_map, sizeof(int32_t) * (size_t)n_users_raw, cudaMemcpyDeviceToHost, s));
+      CKR(mail_wait(c));
+      d->n_users = n_users;
+    }
     uint32_t *iflag, *ipos;
     int32_t *d_item_map;
     CKR(ar.alloc(&iflag, ni + 1));
     CKR(ar.alloc(&ipos, ni + 1));
     CKR(ar.alloc(&d_item_map, ni));
-    CK(cudaMemsetAsync(iflag, 0, sizeof(uint32_t) * ((size_t)ni + 1), s));
-    if (ne > 0)
-      k_ingest_item_flags<<<grid_for(ne, 256, c->sm_count), 256, 0, s>>>(ne, d_user[t], d_item[t], d_user_map, iflag);
+    if (src.keep_item_space) {
+      CK(cudaMemsetAsync(iflag + ni, 0, 4, s));
+      k_fill_u32<<<grid_for(ni, 256, c->sm_count), 256, 0, s>>>(ni, 1u, iflag);
+    } else {
+      CK(cudaMemsetAsync(iflag, 0, sizeof(uint32_t) * ((size_t)ni + 1), s));
+      if (ne > 0) k_ingest_item_flags<<<grid_for(ne, 256, c->sm_count), 256, 0, s>>>(ne, d_user, d_item, d_user_map, iflag);
+    }
     CKR(exclusive_sum_u32(c, ar, iflag, ipos, ni + 1));
-    k_ingest_make_map<<<grid_for(ni, 256, c->sm_count), 256, 0, s>>>(ev[t].n_items_raw, iflag, ipos, d_item_map);
+    k_ingest_make_map<<<grid_for(ni, 256, c->sm_count), 256, 0, s>>>(src.n_items_raw[t], iflag, ipos, d_item_map);
     uint32_t n_items = 0;
-    CKR(mail_fetch(c, &n_items, ipos + ev[t].n_items_raw, 4));
-    if (ev[t].n_items_raw > 0)
-      CK(cudaMemcpyAsync(item_maps[t], d_item_map, sizeof(int32_t) * (size_t)ev[t].n_items_raw, cudaMemcpyDeviceToHost, s));
+    CKR(mail_fetch(c, &n_items, ipos + src.n_items_raw[t], 4));
+    if (src.n_items_raw[t] > 0 && item_maps && item_maps[t])
+      CK(cudaMemcpyAsync(item_maps[t], d_item_map, sizeof(int32_t) * (size_t)src.n_items_raw[t], cudaMemcpyDeviceToHost, s));
     // sort surviving (user, item) keys, drop duplicates, rebuild row_ptr
     unsigned long long *k0, *k1, *d_kept;
     CKR(ar.alloc(&k0, std::max<long long>(ne, 1)));
     CKR(ar.alloc(&k1, std::max<long long>(ne, 1)));
     CKR(ar.alloc(&d_kept, 1));
     CK(cudaMemsetAsync(d_kept, 0, 8, s));
-    if (ne > 0)
-      k_ingest_keys<<<grid_for(ne, 256, c->sm_count), 256, 0, s>>>(ne, d_user[t], d_item[t], d_user_map, d_item_map, k0, d_kept);
+    if (ne > 0) k_ingest_keys<<<grid_for(ne, 256, c->sm_count), 256, 0, s>>>(ne, d_user, d_item, d_user_map, d_item_map, k0, d_kept);
     c->launches += 3;
     unsigned long long kept = 0;
     CKR(mail_fetch(c, &kept, d_kept, 8));
     CKR(mail_wait(c));
+    ar.release(d_user);   // the raw events are dead once the keys exist
+    ar.release(d_item);
     d->n_cols[t] = n_items;
     void *p = nullptr;
     cudaError_t e = cudaMallocAsync(&p, sizeof(int64_t) * ((size_t)n_users + 1), s);
     if (e != cudaSuccess) return set_error(CCO_E_OOM, "cudaMallocAsync row_ptr: %s", cudaGetErrorString(e));
     d->rp[t] = (long long *)p;
+    d->rp_alloc[t] = p;
     e = cudaMallocAsync(&p, sizeof(int32_t) * (size_t)std::max<unsigned long long>(kept, 4), s);
     if (e != cudaSuccess) return set_error(CCO_E_OOM, "cudaMallocAsync col_idx: %s", cudaGetErrorString(e));
     d->col[t] = (int32_t *)p;
+    d->col_alloc[t] = p;
     CK(cudaEventCreateWithFlags(&d->ready[t], cudaEventDisableTiming));
     long long n_unique = 0;
     if (kept > 0) {
+      int row_bits = 1;
+      while ((1LL << row_bits) < (long long)n_users) ++row_bits;
       cub::DoubleBuffer<unsigned long long> db(k0, k1);
       size_t tb = 0;
+      // dropped events carry the key ~0 and sort to the end: all 64 bits take part
       CK(cub::DeviceRadixSort::SortKeys(nullptr, tb, db, (long long)ne, 0, 64, s));
       void *tmp;
       CKR(ar.alloc((char **)&tmp, tb));
@@ -1301,11 +1622,127 @@ int cco_ingest(cco_ctx_t *c, int32_t n_types, const cco_events_t *ev, int64_t n_
     ar.release(k1);
     ar.release(iflag);
     ar.release(ipos);
+    ar.release(d_item_map);
+  }
+  // every rank of a multi-GPU job builds the whole matrices (the events are all here) and then works on its block of
+  // users like an uploaded dataset does; the block sizes (padding of the column-block all-gather) come from row_ptr
+  long long u_lo, u_hi;
+  user_block(n_users, c->world, c->rank, &u_lo, &u_hi);
+  d->row_base = u_lo;
+  d->n_local = u_hi - u_lo;
+  std::vector<std::vector<long long>> edge(n_types, std::vector<long long>((size_t)c->world + 1, 0));
+  for (int t = 0; t < n_types; ++t)
+    for (int q = 0; q <= c->world; ++q) {
+      long long a0, a1;
+      user_block(n_users, c->world, std::min(q, c->world - 1), &a0, &a1);
+      CKR(mail_fetch(c, &edge[t][q], d->rp[t] + (q < c->world ? a0 : a1), 8));
+    }
+  CKR(mail_wait(c));
+  for (int t = 0; t < n_types; ++t) {
+    for (int q = 0; q < c->world; ++q) d->block_cap[t] = std::max(d->block_cap[t], edge[t][q + 1] - edge[t][q]);
+    d->rp[t] += u_lo;   // views of the block; rp_alloc / col_alloc keep the whole matrices
   }
   CK(cudaStreamSynchronize(s));
   CK(cudaGetLastError());
   g.ok = true;
   *out = d;
+  return CCO_OK;
+}
+
+int cco_ingest(cco_ctx_t *c, int32_t n_types, const cco_events_t *ev, int64_t n_users_raw, int32_t min_events_per_user,
+               int32_t *user_map, int32_t *const *item_maps, cco_dataset_t **out) {
+  if (!c || !ev || !user_map || !item_maps || !out || n_types < 1) return set_error(CCO_E_INVALID_ARG, "bad argument");
+  if (n_users_raw < 0 || n_users_raw >= 0x7fffffffLL) return set_error(CCO_E_INVALID_ARG, "n_users_raw out of range");
+  IngestSource src;
+  src.n_types = n_types;
+  src.n_users_raw = n_users_raw;
+  for (int t = 0; t < n_types; ++t) {
+    if (ev[t].n_events < 0 || ev[t].n_events >= 0xffffffffLL || ev[t].n_items_raw < 0)
+      return set_error(CCO_E_INVALID_ARG, "type %d: bad event count / item space", t);
+    if (ev[t].n_events > 0 && (!ev[t].user || !ev[t].item)) return set_error(CCO_E_INVALID_ARG, "type %d: null event arrays", t);
+    if (!item_maps[t] && ev[t].n_items_raw > 0) return set_error(CCO_E_INVALID_ARG, "type %d: null item_map", t);
+    // ids are range-checked on the host: they index device arrays
+    for (int64_t i = 0; i < ev[t].n_events; ++i)
+      if (ev[t].user[i] < 0 || ev[t].user[i] >= n_users_raw || ev[t].item[i] < 0 || ev[t].item[i] >= ev[t].n_items_raw)
+        return set_error(CCO_E_INVALID_ARG, "type %d: user or item id out of range at event %lld", t, (long long)i);
+    src.n_events.push_back(ev[t].n_events);
+    src.n_items_raw.push_back(ev[t].n_items_raw);
+  }
+  cudaStream_t s = c->stream;
+  src.fill = [&](int t, long long *d_user, int32_t *d_item) -> int {
+    CK(cudaMemcpyAsync(d_user, ev[t].user, sizeof(int64_t) * (size_t)ev[t].n_events, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_item, ev[t].item, sizeof(int32_t) * (size_t)ev[t].n_events, cudaMemcpyHostToDevice, s));
+    return CCO_OK;
+  };
+  return ingest_core(c, src, min_events_per_user, user_map, item_maps, out);
+}
+
+// The synthetic workload of bench.py / the tests (SURVEY.md 8d spec; synth.py holds the numpy twin of the stream):
+// event e of a type draws  h1 = mix64(mix64(seed) + (e + 1) * golden), h2 = mix64(h1 ^ 0x6a09e667f3bcc909);
+// user = user_perm[upper_bound(user_cdf, u01(h1))], item = item_perm[upper_bound(item_cdf, u01(h2))]; the events are
+// generated straight into HBM and go through the same ingest as cco_ingest.
+int cco_synth_ingest(cco_ctx_t *c, int32_t n_types, const cco_synth_type_t *types, int64_t n_users_raw, const double *user_cdf,
+                     const int32_t *user_perm, int32_t min_events_per_user, int32_t keep_item_space, cco_dataset_t **out) {
+  if (!c || !types || !out || n_types < 1 || !user_cdf || !user_perm) return set_error(CCO_E_INVALID_ARG, "bad argument");
+  if (n_users_raw < 1 || n_users_raw >= 0x7fffffffLL) return set_error(CCO_E_INVALID_ARG, "n_users_raw out of range");
+  IngestSource src;
+  src.n_types = n_types;
+  src.n_users_raw = n_users_raw;
+  src.keep_item_space = keep_item_space != 0;
+  for (int t = 0; t < n_types; ++t) {
+    if (types[t].n_events < 0 || types[t].n_events >= 0xffffffffLL || types[t].n_items < 1 || !types[t].item_cdf || !types[t].item_perm)
+      return set_error(CCO_E_INVALID_ARG, "type %d: bad generator spec", t);
+    src.n_events.push_back(types[t].n_events);
+    src.n_items_raw.push_back(types[t].n_items);
+  }
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  double *d_ucdf = nullptr, *d_icdf = nullptr;
+  int32_t *d_uperm = nullptr, *d_iperm = nullptr;
+  int32_t max_items = 1;
+  for (int t = 0; t < n_types; ++t) max_items = std::max(max_items, types[t].n_items);
+  auto drop = [&]() {
+    for (void *p : {(void *)d_ucdf, (void *)d_icdf, (void *)d_uperm, (void *)d_iperm})
+      if (p) cudaFreeAsync(p, s);
+  };
+  auto up = [&]() -> int {
+    CK(cudaMallocAsync((void **)&d_ucdf, sizeof(double) * (size_t)n_users_raw, s));
+    CK(cudaMallocAsync((void **)&d_uperm, sizeof(int32_t) * (size_t)n_users_raw, s));
+    CK(cudaMallocAsync((void **)&d_icdf, sizeof(double) * (size_t)max_items, s));
+    CK(cudaMallocAsync((void **)&d_iperm, sizeof(int32_t) * (size_t)max_items, s));
+    CK(cudaMemcpyAsync(d_ucdf, user_cdf, sizeof(double) * (size_t)n_users_raw, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_uperm, user_perm, sizeof(int32_t) * (size_t)n_users_raw, cudaMemcpyHostToDevice, s));
+    return CCO_OK;
+  };
+  int rc = up();
+  if (rc != CCO_OK) { drop(); return rc; }
+  src.fill = [&](int t, long long *d_user, int32_t *d_item) -> int {
+    CK(cudaMemcpyAsync(d_icdf, types[t].item_cdf, sizeof(double) * (size_t)types[t].n_items, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_iperm, types[t].item_perm, sizeof(int32_t) * (size_t)types[t].n_items, cudaMemcpyHostToDevice, s));
+    k_synth_events<<<grid_for(types[t].n_events, 256, c->sm_count), 256, 0, s>>>(types[t].n_events, types[t].seed, d_ucdf, d_uperm,
+                                                                                (int32_t)n_users_raw, d_icdf, d_iperm, types[t].n_items,
+                                                                                d_user, d_item);
+    c->launches++;
+    CK(cudaGetLastError());
+    return CCO_OK;
+  };
+  rc = ingest_core(c, src, min_events_per_user, nullptr, nullptr, out);
+  drop();
+  return rc;
+}
+
+// copy matrix i of a resident dataset into caller-provided host arrays (pinned ones from cco_host_alloc copy at PCIe speed)
+int cco_dataset_copy_to_host(const cco_dataset_t *ds, int32_t i, int64_t *row_ptr, int32_t *col_idx) {
+  if (!ds || !row_ptr || i < 0 || i >= ds->n_mats) return set_error(CCO_E_INVALID_ARG, "bad argument");
+  if (ds->nnz[i] > 0 && !col_idx) return set_error(CCO_E_INVALID_ARG, "null col_idx");
+  if (!ds->whole) return set_error(CCO_E_UNSUPPORTED, "this dataset holds one rank's block of users only");
+  cco_ctx *c = ds->ctx;
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->copy_stream));
+  CK(cudaMemcpyAsync(row_ptr, ds->rp_alloc[i], sizeof(int64_t) * ((size_t)ds->n_users + 1), cudaMemcpyDeviceToHost, c->stream));
+  if (ds->nnz[i] > 0)
+    CK(cudaMemcpyAsync(col_idx, ds->col_alloc[i], sizeof(int32_t) * (size_t)ds->nnz[i], cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
   return CCO_OK;
 }
 
@@ -1435,23 +1872,25 @@ int cco_debug_llr(cco_ctx_t *c, int64_t n, const int64_t *k11, const int64_t *k1
 int cco_debug_downsample(cco_ctx_t *c, const cco_csr_t *m, int32_t max_interactions, int32_t seed, uint32_t flags,
                          int64_t **row_ptr, int32_t **col_idx, int32_t *raw_col_counts, int32_t *new_col_counts) {
   if (!c || !m || !row_ptr || !col_idx) return set_error(CCO_E_INVALID_ARG, "null argument");
+  if (c->world != 1 || !c->members.empty()) return set_error(CCO_E_UNSUPPORTED, "debug entries need a single-GPU context");
   cco_indicator_params_t prm = {max_interactions, 1, 0, 0.0};
   CKR(validate_host(1, m, &prm));
   CK(cudaSetDevice(c->device));
+  mail_reset(c);
   cco_dataset *ds = nullptr;
   CKR(dataset_upload(c, 1, m, flags, &ds));
   struct DG { cco_dataset *d; ~DG() { dataset_release(d); } } dg{ds};
   Arena ar(c->stream);
-  std::vector<DevRaw> raw(1);
-  raw[0].n_rows = ds->n_users; raw[0].n_cols = (int32_t)ds->n_cols[0]; raw[0].nnz = ds->nnz[0];
-  raw[0].rp = ds->rp[0]; raw[0].col = ds->col[0];
+  DevRaw raw;
+  raw.n_rows = ds->n_users; raw.n_cols = (int32_t)ds->n_cols[0]; raw.nnz = ds->nnz[0]; raw.nnz_cap = ds->nnz[0];
+  raw.rp = ds->rp[0]; raw.col = ds->col[0];
   int32_t *counts;
   CKR(ar.alloc(&counts, std::max<int32_t>(m->n_cols, 1)));
   CK(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)std::max<int32_t>(m->n_cols, 1), c->stream));
-  if (raw[0].nnz > 0 && m->n_rows > 0)
-    k_col_histogram<<<grid_for(raw[0].nnz, 256, c->sm_count), 256, 0, c->stream>>>(0, m->n_rows, raw[0].rp, raw[0].col, counts, 1, 0);
+  if (raw.nnz > 0 && m->n_rows > 0)
+    k_col_histogram<<<grid_for(raw.nnz, 256, c->sm_count), 256, 0, c->stream>>>(0, m->n_rows, raw.rp, raw.col, counts, 1, 0);
   DevMat dm;
-  CKR(downsample_device(c, ar, raw[0], counts, max_interactions, seed, flags, &dm));
+  CKR(downsample_device(c, ar, raw, counts, max_interactions, seed, flags, &dm));
   std::vector<uint32_t> rp32((size_t)m->n_rows + 1);
   CK(cudaMemcpyAsync(rp32.data(), dm.rp, sizeof(uint32_t) * rp32.size(), cudaMemcpyDeviceToHost, c->stream));
   if (raw_col_counts && m->n_cols > 0)
@@ -1474,20 +1913,24 @@ int cco_debug_downsample(cco_ctx_t *c, const cco_csr_t *m, int32_t max_interacti
 int cco_debug_cooccurrence(cco_ctx_t *c, const cco_csr_t *a, const cco_csr_t *b, int64_t **row_ptr, int32_t **col_idx,
                            int32_t **count) {
   if (!c || !a || !b || !row_ptr || !col_idx || !count) return set_error(CCO_E_INVALID_ARG, "null argument");
+  if (c->world != 1 || !c->members.empty()) return set_error(CCO_E_UNSUPPORTED, "debug entries need a single-GPU context");
   cco_csr_t two[2] = {*a, *b};
   cco_indicator_params_t prm[2] = {{0x7fffffff, 1, 0, 0.0}, {0x7fffffff, 1, 0, 0.0}};
   CKR(validate_host(2, two, prm));
   CK(cudaSetDevice(c->device));
-  c->mail_pending.clear();
-  c->mail_used = 0;
+  mail_reset(c);
   cudaStream_t s = c->stream;
   cco_dataset *ds = nullptr;
   CKR(dataset_upload(c, 2, two, 0, &ds));
   struct DG { cco_dataset *d; ~DG() { dataset_release(d); } } dg{ds};
   Arena ar(s);
+  struct CopyJoin {
+    cco_ctx *c;
+    ~CopyJoin() { cudaStreamSynchronize(c->copy_stream); }
+  } copy_join{c};
   std::vector<DevRaw> raw(2);
   for (int i = 0; i < 2; ++i) {
-    raw[i].n_rows = ds->n_users; raw[i].n_cols = (int32_t)ds->n_cols[i]; raw[i].nnz = ds->nnz[i];
+    raw[i].n_rows = ds->n_users; raw[i].n_cols = (int32_t)ds->n_cols[i]; raw[i].nnz = ds->nnz[i]; raw[i].nnz_cap = ds->nnz[i];
     raw[i].rp = ds->rp[i]; raw[i].col = ds->col[i];
   }
   // identity "downsample" (m = INT_MAX) gives the device CSR + marginals
@@ -1506,29 +1949,33 @@ int cco_debug_cooccurrence(cco_ctx_t *c, const cco_csr_t *a, const cco_csr_t *b,
   CKR(ar.alloc(&at_ptr, n_items_a + 1));
   CKR(ar.alloc(&cursor, n_items_a + 1));
   CKR(ar.alloc(&marg_pad, n_items_a + 1));
-  CKR(ar.alloc(&d_max, 1));
+  CKR(ar.alloc(&d_max, 2));
   CKR(ar.alloc(&at_users, std::max<long long>(raw[0].nnz, 1)));
-  CK(cudaMemsetAsync(d_max, 0, 4, s));
+  CK(cudaMemsetAsync(d_max, 0, 8, s));
   CK(cudaMemcpyAsync(marg_pad, dm[0].marg, sizeof(int32_t) * (size_t)n_items_a, cudaMemcpyDeviceToDevice, s));
   CK(cudaMemsetAsync(marg_pad + n_items_a, 0, 4, s));
   CKR(exclusive_sum_u32(c, ar, marg_pad, at_ptr, (long long)n_items_a + 1));
   CK(cudaMemcpyAsync(cursor, at_ptr, sizeof(uint32_t) * ((size_t)n_items_a + 1), cudaMemcpyDeviceToDevice, s));
   k_transpose_scatter<<<grid_for(a->n_rows * kSG, 256, c->sm_count), 256, 0, s>>>(a->n_rows, dm[0].rp, dm[0].col, cursor, at_users);
   if (n_items_a > 0) k_max_i32<<<grid_for(n_items_a, 256, c->sm_count, 2), 256, 0, s>>>(n_items_a, dm[0].marg, d_max);
-  int32_t max_marg_a = 0;
-  CK(cudaMemcpyAsync(&max_marg_a, d_max, 4, cudaMemcpyDeviceToHost, s));
+  if (dm[1].n_cols > 0) k_max_i32<<<grid_for(dm[1].n_cols, 256, c->sm_count, 2), 256, 0, s>>>(dm[1].n_cols, dm[1].marg, d_max + 1);
+  int32_t max_marg_ab[2] = {0, 0};
+  CK(cudaMemcpyAsync(max_marg_ab, d_max, 8, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   CK(cudaGetLastError());
   ResultMat rm;
   IndicatorOut io;
+  IndicatorState ist;
+  struct EG { IndicatorState &x; ~EG() { if (x.packed) cudaEventDestroy(x.packed); } } eg{ist};
   cco_indicator_params_t p1 = {0x7fffffff, 1, 0, 0.0};
-  int rc = run_indicator(c, ar, at_ptr, at_users, n_items_a, dm[0].marg, max_marg_a, dm[1], a->n_rows, false, p1, 0, true, 0, 1,
-                         &rm, &io, nullptr);
-  cudaStreamSynchronize(c->copy_stream);
   auto put = [&]() {
     for (void *p : {(void *)rm.row_ptr, (void *)rm.col, (void *)rm.llr, (void *)rm.cnt})
       if (p) c->pinned_put(p);
   };
+  int rc = enqueue_indicator(c, ar, at_ptr, at_users, n_items_a, dm[0].marg, max_marg_ab[0], max_marg_ab[1], dm[1], a->n_rows, false, p1,
+                             0, true, nullptr, nullptr, &ist);
+  if (rc == CCO_OK) rc = finish_indicator(c, &ist, 0, 0, &rm, &io);
+  cudaStreamSynchronize(c->copy_stream);
   if (rc != CCO_OK) {
     put();
     return rc;

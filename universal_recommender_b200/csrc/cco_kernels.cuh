@@ -33,6 +33,8 @@ struct RowArgs {
   const int32_t *b_col;
   const int32_t *marg_a;  // colA, downsampled, per primary item
   const int32_t *marg_b;  // colB, downsampled, per column of B'
+  const uint2 *ext;       // experiment (tools/experiments/cco_rows2.cuh): (start, len) of B'[u] per (item, user) pair; unused
+  int32_t max_marg_b;     // largest colB (bounds every co-occurrence count together with rowA)
   // schedule: items sorted by estimated work, descending; bin b = rows_sorted[bin_bounds[b], bin_bounds[b+1])
   const int32_t *rows_sorted;
   const uint32_t *row_work;  // by item: w_a = sum_{u in a} degB'(u), saturated at 2^32-1
@@ -229,19 +231,22 @@ __device__ __forceinline__ bool keep_entry(long long d, double row_rate, int32_t
   return sample_u01(seed, row, j) <= rate;
 }
 
-// pass 1 of sampleDownAndBinarize: kept entries per row + post-sample column marginals
-__global__ void k_downsample_count(long long row_begin, long long n_rows, const long long *__restrict__ rp, const int32_t *__restrict__ col,
+// pass 1 of sampleDownAndBinarize: kept entries per row + post-sample column marginals.
+// The matrix handed in is a block of n_local user rows (the whole matrix on one GPU, this rank's user block otherwise);
+// row_base = global index of its first user: the sampler hashes GLOBAL user ids and kept_per_row is indexed globally.
+__global__ void k_downsample_count(long long n_local, long long row_base, const long long *__restrict__ rp, const int32_t *__restrict__ col,
                                    const int32_t *__restrict__ raw_counts, int32_t m, int32_t seed, uint32_t flags,
                                    uint32_t *__restrict__ kept_per_row, int32_t *__restrict__ new_counts) {
   const int lane = threadIdx.x % kSG;
   const unsigned sg_mask = ((1u << kSG) - 1u) << ((threadIdx.x & 31) / kSG * kSG);
-  long long row = row_begin + (blockIdx.x * (long long)blockDim.x + threadIdx.x) / kSG;  // rows [row_begin, n_rows)
+  long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / kSG;
   const long long stride = (long long)gridDim.x * blockDim.x / kSG;
   const bool intdiv = (flags & CCO_FLAG_ROWRATE_INTDIV) != 0;
   // all lanes of a sub-group share `row`, so loop trip counts are sub-group uniform
-  for (; row < n_rows; row += stride) {
+  for (; row < n_local; row += stride) {
     long long s = rp[row], e = rp[row + 1], d = e - s;
     const double row_rate = row_sample_rate(d, m, intdiv);
+    const uint32_t g = (uint32_t)(row_base + row);
     uint32_t kept = 0;
     for (long long q0 = s; q0 < e; q0 += kSG) {
       long long q = q0 + lane;
@@ -249,41 +254,58 @@ __global__ void k_downsample_count(long long row_begin, long long n_rows, const 
       int32_t j = 0;
       if (q < e) {
         j = col[q];
-        keep = keep_entry(d, row_rate, raw_counts[j], m, seed, (uint32_t)row, (uint32_t)j);
+        keep = keep_entry(d, row_rate, raw_counts[j], m, seed, g, (uint32_t)j);
       }
       if (keep && new_counts) atomicAdd(&new_counts[j], 1);
       kept += __popc(__ballot_sync(sg_mask, keep) & sg_mask);
     }
-    if (lane == 0) kept_per_row[row] = kept;
+    if (lane == 0) kept_per_row[g] = kept;
   }
 }
 
-// pass 2: ordered compaction (ascending columns are preserved)
-__global__ void k_downsample_write(long long row_begin, long long n_rows, const long long *__restrict__ rp, const int32_t *__restrict__ col,
+// pass 2: ordered compaction (ascending columns are preserved).  new_ptr is the GLOBAL row pointer of the sampled
+// matrix; out_base (nullable) points at the entry the output buffer starts at (this rank's block offset when the block is
+// written into a send buffer, null = 0 when it is written in place).
+__global__ void k_downsample_write(long long n_local, long long row_base, const long long *__restrict__ rp, const int32_t *__restrict__ col,
                                    const int32_t *__restrict__ raw_counts, int32_t m, int32_t seed, uint32_t flags,
-                                   const uint32_t *__restrict__ new_ptr, int32_t *__restrict__ new_col) {
+                                   const uint32_t *__restrict__ new_ptr, const uint32_t *__restrict__ out_base, int32_t *__restrict__ new_col) {
   const int lane = threadIdx.x % kSG;
   const int sg_shift = (threadIdx.x & 31) / kSG * kSG;
   const unsigned sg_mask = ((1u << kSG) - 1u) << sg_shift;
-  long long row = row_begin + (blockIdx.x * (long long)blockDim.x + threadIdx.x) / kSG;  // rows [row_begin, n_rows)
+  long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / kSG;
   const long long stride = (long long)gridDim.x * blockDim.x / kSG;
   const bool intdiv = (flags & CCO_FLAG_ROWRATE_INTDIV) != 0;
-  for (; row < n_rows; row += stride) {
+  const uint32_t base = out_base ? *out_base : 0u;
+  for (; row < n_local; row += stride) {
     long long s = rp[row], e = rp[row + 1], d = e - s;
     const double row_rate = row_sample_rate(d, m, intdiv);
-    uint32_t w = new_ptr[row];
+    const uint32_t g = (uint32_t)(row_base + row);
+    uint32_t w = new_ptr[g] - base;
     for (long long q0 = s; q0 < e; q0 += kSG) {
       long long q = q0 + lane;
       bool keep = false;
       int32_t j = 0;
       if (q < e) {
         j = col[q];
-        keep = keep_entry(d, row_rate, raw_counts[j], m, seed, (uint32_t)row, (uint32_t)j);
+        keep = keep_entry(d, row_rate, raw_counts[j], m, seed, g, (uint32_t)j);
       }
       unsigned b = (__ballot_sync(sg_mask, keep) & sg_mask) >> sg_shift;
       if (keep) new_col[w + __popc(b & ((1u << lane) - 1u))] = j;
       w += __popc(b);
     }
+  }
+}
+
+// multi-GPU: every rank sampled its user block into a padded send buffer; after the all-gather the W padded blocks
+// (cap entries apart) are packed into the contiguous column array of the sampled matrix.  Block q holds users
+// [q * S, min((q + 1) * S, U)): its length is new_ptr[end] - new_ptr[begin], read here -- no host round trip.
+__global__ void k_pack_blocks(int world, long long S, long long U, long long cap, const uint32_t *__restrict__ new_ptr,
+                              const int32_t *__restrict__ gathered, int32_t *__restrict__ new_col) {
+  for (int q = blockIdx.y; q < world; q += gridDim.y) {
+    const long long u0 = min((long long)q * S, U), u1 = min(u0 + S, U);
+    const uint32_t lo = new_ptr[u0], hi = new_ptr[u1];
+    const int32_t *src = gathered + (long long)q * cap;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < hi - lo; i += gridDim.x * blockDim.x) new_col[lo + i] = src[i];
   }
 }
 
@@ -302,7 +324,8 @@ __global__ void k_transpose_scatter(long long n_rows, const uint32_t *__restrict
 // w_a = sum over users of item a of degB'(u)  (= products of output row a), saturating; also P
 __global__ void k_row_work(int32_t n_items, const uint32_t *__restrict__ at_ptr, const int32_t *__restrict__ at_users,
                            const uint32_t *__restrict__ b_ptr, uint32_t *__restrict__ row_work,
-                           unsigned long long *__restrict__ work64, int32_t *__restrict__ item_ids) {
+                           unsigned long long *__restrict__ work64, int32_t *__restrict__ item_ids,
+                           uint2 *__restrict__ ext) {
   const int lane = threadIdx.x % kSG;
   const unsigned sg_mask = ((1u << kSG) - 1u) << ((threadIdx.x & 31) / kSG * kSG);
   int item = (blockIdx.x * blockDim.x + threadIdx.x) / kSG;
@@ -312,7 +335,9 @@ __global__ void k_row_work(int32_t n_items, const uint32_t *__restrict__ at_ptr,
     unsigned long long w = 0;
     for (uint32_t q = s + lane; q < e; q += kSG) {
       int32_t u = at_users[q];
-      w += b_ptr[u + 1] - b_ptr[u];
+      const uint32_t bs = b_ptr[u], bl = b_ptr[u + 1] - bs;
+      w += bl;
+      if (ext) ext[q] = make_uint2(bs, bl);   // the row kernel streams these instead of gathering b_ptr twice per user
     }
 #pragma unroll
     for (int o = kSG / 2; o > 0; o >>= 1) w += __shfl_xor_sync(sg_mask, w, o);
@@ -334,8 +359,9 @@ __global__ void k_bin_bounds(int32_t n_rows, const uint32_t *__restrict__ sorted
   int b = threadIdx.x;
   if (b > n_bins) return;
   if (b == 0) { bounds[0] = 0; return; }
-  // first index whose work <= thresholds[b-1]  (sorted descending)
-  uint32_t t = thresholds.t[b - 1];
+  // first index whose work <= thresholds[b-1]  (sorted descending).  The last bin ends at the first row WITHOUT work:
+  // rows of other ranks (masked to zero by k_mask_work) and empty rows need no kernel, their out_len is preset to 0.
+  uint32_t t = b == n_bins ? 0u : thresholds.t[b - 1];
   int lo = 0, hi = n_rows;
   while (lo < hi) {
     int mid = (lo + hi) >> 1;
@@ -441,7 +467,9 @@ __device__ int reduce_candidates(uint4 *tk, uint4 *aux, int n, int k, int M, int
       else if (nb < 64) match = w0 == pre0 && (w1 >> (64 - nb)) == (pre1 >> (64 - nb));
       else if (nb == 64) match = w0 == pre0 && w1 == pre1;
       else match = w0 == pre0 && w1 == pre1 && (w2 >> (96 - nb)) == (pre2 >> (96 - nb));
-      if (match) atomicAdd(&hist[(cand_word(e, wi) >> sh) & 255u], 1);
+      // digit = byte (sh / 8) of the key word, extracted with PRMT: ptxas 12.9 turned `(word >> 24) & 255` of the
+      // peeled nb == 0 pass into an index by the WHOLE word in one inlining context (compute-sanitizer: invalid shared atomic)
+      if (match) atomicAdd(&hist[__byte_perm(cand_word(e, wi), 0u, 0x4440u | (uint32_t)(sh >> 3))], 1);
     }
     group_sync<GROUP>();
     if (gtid < 32) {
@@ -514,7 +542,7 @@ __device__ int reduce_candidates(uint4 *tk, uint4 *aux, int n, int k, int M, int
   return kept;
 }
 
-constexpr int kCutBins = 1024;  // level-1 integer cut: colB histogram bins (cells with colB >= kCutBins are never cut)
+constexpr int kCutBins = 512;   // level-1 integer cut: u16 colB bins; they alias the 1 KB radix-select histogram (dead until the score loop)
 constexpr int kDomLevels = 15;  // dominance filter keeps cfail[1..15] in ctrl[41..55]
 constexpr int kX12N = 31;  // x12tab[j] = xLogX(ra - j) for j < 31; x12tab[31] = xLogX(N - ra)
 
@@ -557,8 +585,8 @@ __global__ void __launch_bounds__(GROUP == 32 ? 256 : GROUP) k_rows(const RowArg
   int *ctrl = reinterpret_cast<int *>(x11tab + 32);  // [0] ncand [1] have_thr [4..7] threshold entry [16..27] select state [40..55] dominance frontier [64..64+NW) per-warp list sizes
   int *hist = ctrl + 128;                                     // 256 bins of the radix select
   uint32_t *wqueue = reinterpret_cast<uint32_t *>(hist + 256);  // NW * 64 queued cells awaiting evaluation
-  uint32_t *h1 = wqueue + NW * 64;   // kCutBins/2 words: u16 histogram of colB over the strongly positive k11 == 1 cells
-  uint32_t *table = h1 + kCutBins / 2;
+  uint32_t *h1 = reinterpret_cast<uint32_t *>(hist);   // kCutBins/2 words: u16 histogram of colB over the strongly positive k11 == 1 cells
+  uint32_t *table = wqueue + NW * 64;
   volatile int *vctrl = ctrl;
 
   const int row_begin = a.bin_bounds[a.bin], row_end = a.bin_bounds[a.bin + 1];
@@ -701,9 +729,9 @@ __global__ void __launch_bounds__(GROUP == 32 ? 256 : GROUP) k_rows(const RowArg
         }
         group_sync<GROUP>();
         if (gtid < 32) {
-          // lane l owns bins [32 l, 32 l + 32): 16 words
+          // lane l owns bins [16 l, 16 l + 16): 8 words
           uint32_t sum = 0;
-          for (int wi = 0; wi < 16; ++wi) { const uint32_t v = h1[gtid * 16 + wi]; sum += (v & 0xffffu) + (v >> 16); }
+          for (int wi = 0; wi < 8; ++wi) { const uint32_t v = h1[gtid * 8 + wi]; sum += (v & 0xffffu) + (v >> 16); }
           uint32_t incl = sum;
 #pragma unroll
           for (int d = 1; d < 32; d <<= 1) {
@@ -714,12 +742,12 @@ __global__ void __launch_bounds__(GROUP == 32 ? 256 : GROUP) k_rows(const RowArg
           int found = 0x7fffffff;
           if (excl < (uint32_t)a.top_k && incl >= (uint32_t)a.top_k) {
             uint32_t run = excl;
-            for (int wi = 0; wi < 16 && found == 0x7fffffff; ++wi) {
-              const uint32_t v = h1[gtid * 16 + wi];
+            for (int wi = 0; wi < 8 && found == 0x7fffffff; ++wi) {
+              const uint32_t v = h1[gtid * 8 + wi];
               run += v & 0xffffu;
-              if (run >= (uint32_t)a.top_k) { found = gtid * 32 + 2 * wi; break; }
+              if (run >= (uint32_t)a.top_k) { found = gtid * 16 + 2 * wi; break; }
               run += v >> 16;
-              if (run >= (uint32_t)a.top_k) { found = gtid * 32 + 2 * wi + 1; break; }
+              if (run >= (uint32_t)a.top_k) { found = gtid * 16 + 2 * wi + 1; break; }
             }
           }
 #pragma unroll
@@ -755,7 +783,7 @@ __global__ void __launch_bounds__(GROUP == 32 ? 256 : GROUP) k_rows(const RowArg
               const long long cb = a.marg_b[b];
               const bool pos_side = (unsigned long long)ra * (unsigned long long)cb < (unsigned long long)k11 * (unsigned long long)N;
               surv = !(pos_side && k11 <= (uint32_t)kDomLevels && (int)cb >= vctrl[40 + k11]);
-              if (k11 == 1u && (int)cb > cut1 && cb < kCutBins && 2ull * (unsigned long long)ra * (unsigned long long)cb < (unsigned long long)N)
+              if (k11 == 1u && (int)cb > cut1 && 2ull * (unsigned long long)ra * (unsigned long long)cb < (unsigned long long)N)
                 surv = false;   // beyond the level-1 integer cut
             }
           }
@@ -803,18 +831,33 @@ __global__ void __launch_bounds__(GROUP == 32 ? 256 : GROUP) k_rows(const RowArg
         }
         qn -= take;
         const unsigned m = __ballot_sync(0xffffffffu, pass_ok);
+        int basepos_round = 0;
         if (m) {
           int basepos = 0;
           if (lane == 0) basepos = atomicAdd(&ctrl[0], __popc(m));
           basepos = __shfl_sync(0xffffffffu, basepos, 0);
           if (pass_ok) tk[basepos + __popc(m & ((1u << lane) - 1u))] = e;
+          basepos_round = basepos;
         }
         const bool more = qn > 0 || pos < n_mine;
-        bool any_more;
-        if (GROUP == 32) { __syncwarp(); any_more = more; }
-        else any_more = __syncthreads_or(more ? 1 : 0) != 0;
-        const int n = vctrl[0];
-        if (n > prune_limit) {
+        // Both decisions of this round are taken from barrier results (CTA-uniform by construction).  Re-reading ctrl[0]
+        // after the barrier raced with warps that had already looped back and appended (or with warp 0's single-warp
+        // select storing the kept count): warps of one CTA could disagree on `n > prune_limit` and pair different
+        // barriers.  `mine` = the counter right after this warp's own append (0 if it appended nothing): the counter only
+        // grows inside a round, so the largest `mine` is its final value.
+        int mine = 0;
+        if (m) mine = basepos_round + __popc(m);
+        bool any_more, need_prune;
+        if (GROUP == 32) {
+          __syncwarp();
+          any_more = more;
+          need_prune = mine > prune_limit;
+        } else {
+          any_more = __syncthreads_or(more ? 1 : 0) != 0;
+          need_prune = __syncthreads_or(mine > prune_limit ? 1 : 0) != 0;
+        }
+        if (need_prune) {
+          const int n = vctrl[0];   // nobody appends until every warp has left this branch
           if (GROUP > 32 && n <= 512) {
             // small buffer: one warp runs the whole select (no CTA barriers inside), the others wait once
             if (gw == 0) reduce_candidates<32>(tk, aux, n, a.top_k, a.keep_max, hist, ctrl, lane);
@@ -866,23 +909,22 @@ __global__ void __launch_bounds__(GROUP == 32 ? 256 : GROUP) k_rows(const RowArg
   if (lane == 0 && evaluated_local) atomicAdd(a.stat_evaluated, evaluated_local);
 }
 
-// packed output: gather the strided per-row results into CSR order
-__global__ void k_compact_rows(int32_t row_lo, int32_t n_rows, int32_t stride, const long long *__restrict__ out_ptr,
-                               const int32_t *__restrict__ len, const int32_t *__restrict__ col,
-                               const double *__restrict__ llr, const int32_t *__restrict__ cnt,
+// packed output: gather the strided per-row results into CSR order (out_ptr = exclusive scan of the masked row lengths:
+// rows outside this rank's range have length 0 there and are skipped)
+__global__ void k_compact_rows(int32_t n_items, int32_t stride, const long long *__restrict__ out_ptr,
+                               const int32_t *__restrict__ col, const double *__restrict__ llr, const int32_t *__restrict__ cnt,
                                int32_t *__restrict__ p_col, double *__restrict__ p_llr, int32_t *__restrict__ p_cnt) {
   // one warp per row
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   int nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (int r = warp; r < n_rows; r += nwarps) {
-    int item = row_lo + r;
-    int n = len[item];
-    long long o = out_ptr[r];
+  for (int item = warp; item < n_items; item += nwarps) {
+    const long long o = out_ptr[item];
+    const int n = (int)(out_ptr[item + 1] - o);
     size_t src = (size_t)item * stride;
     for (int i = lane; i < n; i += 32) {
       p_col[o + i] = col[src + i];
       if (p_llr) p_llr[o + i] = llr[src + i];
-      p_cnt[o + i] = cnt[src + i];
+      if (p_cnt) p_cnt[o + i] = cnt[src + i];
     }
   }
 }
@@ -893,9 +935,10 @@ __global__ void k_expand_keys(long long n_rows, const long long *__restrict__ rp
   const int lane = threadIdx.x % kSG;
   long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / kSG;
   const long long stride = (long long)gridDim.x * blockDim.x / kSG;
+  const long long q_base = rp[0];   // a rank's user block keeps the caller's absolute offsets
   for (; row < n_rows; row += stride) {
     long long s = rp[row], e = rp[row + 1];
-    for (long long q = s + lane; q < e; q += kSG) keys[q] = ((unsigned long long)row << 32) | (uint32_t)col[q];
+    for (long long q = s + lane; q < e; q += kSG) keys[q - q_base] = ((unsigned long long)row << 32) | (uint32_t)col[q];
   }
 }
 __global__ void k_unique_flags(long long n, const unsigned long long *__restrict__ keys, uint32_t *__restrict__ flag) {
@@ -988,6 +1031,34 @@ __global__ void k_ingest_keys(long long n, const long long *__restrict__ user, c
   if ((threadIdx.x & 31) == 0 && kept) atomicAdd(n_kept, kept);
 }
 
+__global__ void k_fill_u32(long long n, uint32_t v, uint32_t *__restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) out[i] = v;
+}
+
+// ---- synthetic event streams (bench.py / tests; SURVEY.md 8d spec, numpy twin in synth.py) ---------------------------
+// inclusive normalised CDF over ranks -> first rank whose CDF value exceeds u (numpy searchsorted side="right"), clipped
+__device__ __forceinline__ int32_t cdf_upper_bound(const double *__restrict__ cdf, int32_t n, double u) {
+  int32_t lo = 0, hi = n;
+  while (lo < hi) {
+    const int32_t mid = (int32_t)(((uint32_t)lo + (uint32_t)hi) >> 1);
+    if (cdf[mid] <= u) lo = mid + 1; else hi = mid;
+  }
+  return lo < n ? lo : n - 1;
+}
+__global__ void k_synth_events(long long n_events, unsigned long long seed, const double *__restrict__ user_cdf,
+                               const int32_t *__restrict__ user_perm, int32_t n_users, const double *__restrict__ item_cdf,
+                               const int32_t *__restrict__ item_perm, int32_t n_items, long long *__restrict__ user,
+                               int32_t *__restrict__ item) {
+  const uint64_t base = mix64(seed);
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n_events; e += (long long)gridDim.x * blockDim.x) {
+    const uint64_t h1 = mix64(base + (uint64_t)(e + 1) * 0x9e3779b97f4a7c15ULL);
+    const uint64_t h2 = mix64(h1 ^ 0x6a09e667f3bcc909ULL);
+    const double u1 = __dmul_rn((double)(h1 >> 11), 0x1.0p-53), u2 = __dmul_rn((double)(h2 >> 11), 0x1.0p-53);
+    user[e] = user_perm[cdf_upper_bound(user_cdf, n_users, u1)];
+    item[e] = item_perm[cdf_upper_bound(item_cdf, n_items, u2)];
+  }
+}
+
 __global__ void k_max_i32(long long n, const int32_t *__restrict__ x, int32_t *__restrict__ out) {
   int32_t m = 0;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -996,8 +1067,42 @@ __global__ void k_max_i32(long long n, const int32_t *__restrict__ x, int32_t *_
   if ((threadIdx.x & 31) == 0) atomicMax(out, m);
 }
 
-__global__ void k_len_to_i64(int32_t row_lo, int32_t n, const int32_t *__restrict__ len, long long *__restrict__ out) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = len[row_lo + i];
+// rank partition on the device: work of the rows outside this rank's [bounds[rank], bounds[rank + 1]) becomes 0, so they
+// sort behind every row with work and fall out of the last bin; no bound ever travels to the host before the kernels run
+__global__ void k_mask_work(int32_t n_items, const uint32_t *__restrict__ row_work, const int32_t *__restrict__ bounds, int rank,
+                            uint32_t *__restrict__ masked) {
+  const int32_t lo = bounds ? bounds[rank] : 0, hi = bounds ? bounds[rank + 1] : n_items;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += gridDim.x * blockDim.x)
+    masked[i] = (i >= lo && i < hi) ? row_work[i] : 0u;
+}
+
+// kept-cell counts of this rank's rows as int64 (0 outside its range), input of the exclusive scan that gives row_ptr
+__global__ void k_len_to_i64(int32_t n_items, const int32_t *__restrict__ len, const int32_t *__restrict__ bounds, int rank,
+                             long long *__restrict__ out) {
+  const int32_t lo = bounds ? bounds[rank] : 0, hi = bounds ? bounds[rank + 1] : n_items;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= n_items; i += gridDim.x * blockDim.x)
+    out[i] = (i >= lo && i < hi) ? len[i] : 0;
+}
+
+// what the host needs from one indicator, in one mailbox record: [0] row_lo [1] row_hi [2] kept cells [3] products of the
+// range [4] distinct cells [5] evaluated cells [6] hash-overflow flag
+__global__ void k_indicator_record(int32_t n_items, const int32_t *__restrict__ bounds, int rank, const long long *__restrict__ out_ptr,
+                                   const long long *__restrict__ work_prefix, const unsigned long long *__restrict__ distinct_eval,
+                                   const int *__restrict__ err, long long *__restrict__ rec) {
+  if (threadIdx.x || blockIdx.x) return;
+  const int32_t lo = bounds ? bounds[rank] : 0, hi = bounds ? bounds[rank + 1] : n_items;
+  rec[0] = lo;
+  rec[1] = hi;
+  rec[2] = out_ptr[n_items];
+  rec[3] = work_prefix[hi] - work_prefix[lo];
+  rec[4] = (long long)distinct_eval[0];
+  rec[5] = (long long)distinct_eval[1];
+  rec[6] = *err;
+}
+
+// group (single-process multi-GPU) mode: rebase this rank's row pointers by the cells of the ranks before it
+__global__ void k_add_i64(long long n, long long v, long long *__restrict__ x) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) x[i] += v;
 }
 
 }  // namespace cco

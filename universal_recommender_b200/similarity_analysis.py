@@ -118,7 +118,9 @@ class CcoContext:
         return (N.ParamsT * len(params))(*[N.ParamsT(int(m), int(k), 0 if ml is None else 1, 0.0 if ml is None else float(ml))
                                            for (m, k, ml) in params])
 
-    def _collect(self, res, n, copy_arrays=True):
+    def _collect(self, res, n, copy_arrays=True, keep=False):
+        """copy_arrays: numpy copies of the result arrays (default).  keep=True: zero-copy VIEWS of the library-owned pinned
+        result buffers instead; the caller must call free_result(handle) when done (returns (views, handle))."""
         L = self._L
         try:
             out = []
@@ -128,12 +130,16 @@ class CcoContext:
                 nr, nc = C.c_int64(), C.c_int32()
                 prp, pci, pll, pcn = C.POINTER(C.c_int64)(), C.POINTER(C.c_int32)(), C.POINTER(C.c_double)(), C.POINTER(C.c_int32)()
                 N.check(L.cco_result_matrix(res, i, C.byref(nr), C.byref(nc), C.byref(prp), C.byref(pci), C.byref(pll), C.byref(pcn)))
-                rp = np.ctypeslib.as_array(prp, shape=(nr.value + 1,)).copy()
+                rp = np.ctypeslib.as_array(prp, shape=(nr.value + 1,))
+                if not keep:
+                    rp = rp.copy()
                 nnz = int(rp[-1])
-                if nnz and copy_arrays:
-                    ci = np.ctypeslib.as_array(pci, shape=(nnz,)).copy()
-                    ll = np.ctypeslib.as_array(pll, shape=(nnz,)).copy()
-                    cn = np.ctypeslib.as_array(pcn, shape=(nnz,)).copy()
+                if nnz and (copy_arrays or keep):
+                    ci = np.ctypeslib.as_array(pci, shape=(nnz,))
+                    ll = np.ctypeslib.as_array(pll, shape=(nnz,)) if pll else np.zeros(0, np.float64)
+                    cn = np.ctypeslib.as_array(pcn, shape=(nnz,)) if pcn else np.zeros(0, np.int32)
+                    if not keep:
+                        ci, ll, cn = ci.copy(), ll.copy(), cn.copy()
                 else:
                     ci, ll, cn = np.zeros(0, np.int32), np.zeros(0, np.float64), np.zeros(0, np.int32)
                 out.append((rb.value, re_.value, nc.value, rp, ci, ll, cn))
@@ -142,19 +148,27 @@ class CcoContext:
             self.last_stats = TrainStats(st.n_users, st.nnz_in_total, list(st.nnz_downsampled)[:n], list(st.products)[:n],
                                          list(st.distinct_cells)[:n], list(st.out_nnz)[:n], list(st.llr_evaluated)[:n], st.ms_h2d, st.ms_prepare,
                                          st.ms_cooccurrence, st.ms_total, list(st.ms_indicator)[:n], st.n_kernel_launches)
+            if keep:
+                h, res = res, None
+                return out, h
             return out
         finally:
-            L.cco_result_free(res)
+            if res is not None:
+                L.cco_result_free(res)
+
+    def free_result(self, handle):
+        self._L.cco_result_free(handle)
 
     def train_csr(self, mats: Sequence[tuple[int, int, np.ndarray, np.ndarray]], params: Sequence[tuple[int, int, Optional[float]]],
-                  seed: int, flags: int = 0, copy_arrays: bool = True):
+                  seed: int, flags: int = 0, copy_arrays: bool = True, keep: bool = False):
         """Raw entry (cco_train): mats = [(n_rows, n_cols, row_ptr int64, col_idx int32)], params = [(m, k, minLLR|None)].
-        -> list of (row_begin, row_end, n_cols, row_ptr, col_idx, llr, count) numpy copies, one per matrix."""
-        cm, keep = self._csr_array(mats)
+        -> list of (row_begin, row_end, n_cols, row_ptr, col_idx, llr, count) numpy copies, one per matrix
+        (keep=True: zero-copy views + a handle for free_result)."""
+        cm, alive = self._csr_array(mats)
         res = C.c_void_p()
         N.check(self._L.cco_train(self._h, len(mats), cm, self._params_array(params), C.c_int32(_to_i32(seed)), flags,
                                   C.byref(res)))
-        return self._collect(res, len(mats), copy_arrays)
+        return self._collect(res, len(mats), copy_arrays, keep)
 
     # ---- split form: matrices resident in HBM across trains ---------------------------------------------
     def upload(self, mats, flags: int = 0):
@@ -186,6 +200,40 @@ class CcoContext:
         N.check(self._L.cco_ingest(self._h, n, ev, n_users_raw, min_events_per_user, user_map.ctypes.data_as(C.POINTER(C.c_int32)),
                                    maps, C.byref(ds)))
         return (ds, n), user_map[:n_users_raw], [m[:ni] for m, (_, _, ni) in zip(item_maps, events)]
+
+    def synth_dataset(self, types, n_users_raw: int, user_cdf: np.ndarray, user_perm: np.ndarray, min_events_per_user: int = 0,
+                      raw_item_space: bool = False):
+        """Bench/test utility (cco_synth_ingest): the synthetic event streams of synth.py generated in HBM and ingested there.
+        types = [(n_events, seed, item_cdf float64[], item_perm int32[])].  -> resident dataset for train_dataset."""
+        n = len(types)
+        keep, tt = [], (N.SynthTypeT * n)()
+        for t, (ne, seed, icdf, iperm) in enumerate(types):
+            icdf = np.ascontiguousarray(icdf, dtype=np.float64)
+            iperm = np.ascontiguousarray(iperm, dtype=np.int32)
+            keep.append((icdf, iperm))
+            tt[t] = N.SynthTypeT(int(ne), int(seed), len(icdf), 0, icdf.ctypes.data_as(C.POINTER(C.c_double)),
+                                 iperm.ctypes.data_as(C.POINTER(C.c_int32)))
+        ucdf = np.ascontiguousarray(user_cdf, dtype=np.float64)
+        uperm = np.ascontiguousarray(user_perm, dtype=np.int32)
+        ds = C.c_void_p()
+        N.check(self._L.cco_synth_ingest(self._h, n, tt, n_users_raw, ucdf.ctypes.data_as(C.POINTER(C.c_double)),
+                                         uperm.ctypes.data_as(C.POINTER(C.c_int32)), min_events_per_user, 1 if raw_item_space else 0,
+                                         C.byref(ds)))
+        return (ds, n)
+
+    def dataset_shape(self, dataset, i: int):
+        nr, nc, nnz = C.c_int64(), C.c_int32(), C.c_int64()
+        N.check(self._L.cco_dataset_shape(dataset[0], i, C.byref(nr), C.byref(nc), C.byref(nnz)))
+        return nr.value, nc.value, nnz.value
+
+    def dataset_to_host(self, dataset, i: int, pinned: bool = True):
+        """(n_rows, n_cols, row_ptr, col_idx) of matrix i of a resident dataset in (pinned) host arrays."""
+        nr, nc, nnz = self.dataset_shape(dataset, i)
+        rp = self.host_array(nr + 1, np.int64) if pinned else np.zeros(nr + 1, np.int64)
+        ci = self.host_array(nnz, np.int32) if pinned else np.zeros(max(nnz, 1), np.int32)[:nnz]
+        N.check(self._L.cco_dataset_copy_to_host(dataset[0], i, rp.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                 ci.ctypes.data_as(C.POINTER(C.c_int32)) if nnz else None))
+        return nr, nc, rp, ci
 
     def dataset_matrix(self, dataset, i: int):
         """(n_rows, n_cols, row_ptr, col_idx) of matrix i of a resident dataset, copied to the host (tests)."""
