@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define CCO_ABI_VERSION 1
+#define CCO_ABI_VERSION 2
 
 typedef enum {
   CCO_OK = 0,
@@ -68,6 +68,16 @@ typedef struct {
 
 #define CCO_MAX_TOP_K 2048
 
+/*
+ * Limits (each one is a clean CCO_E_UNSUPPORTED with a message, never a wrong result):
+ *  - top_k <= CCO_MAX_TOP_K;  stored entries per matrix < 2^32;  n_rows < 2^31 - 1 (Mahout row keys are Int).
+ *  - packed accumulator word: a row's co-occurrence counts live in shared memory as (column << count_bits | count) in
+ *    32 bits.  count <= min(largest primary-item marginal, largest column marginal of this event type) must fit next to
+ *    the column id: bitlen(n_cols + 1) + bitlen(max count) <= 32.  After the reference's default downsampling (500) every
+ *    marginal is <= ~560, i.e. 10 bits: item spaces up to 4M columns.  Without downsampling (m huge) a 1M-column space
+ *    allows counts < 4096.
+ */
+
 /* cco_train flags */
 enum {
   /* Row sample rate of sampleDownAndBinarize: 0 = real min(m,d)/d (default); 1 = literal
@@ -80,7 +90,12 @@ enum {
   CCO_FLAG_ASSUME_CANONICAL = 4,
   /* measurement only: leave the packed indicator arrays in HBM (col/llr/count host arrays are not
    * filled; row_ptr is).  Used for the device-resident throughput number of bench.py. */
-  CCO_FLAG_RESULT_ON_DEVICE = 8
+  CCO_FLAG_RESULT_ON_DEVICE = 8,
+  /* result contents.  The reference consumer keeps only the ordered column ids of each row (package.scala:100-108
+   * drops the LLR values, nothing reads k11): NO_COUNT skips the count array (cco_result_matrix returns NULL for it),
+   * NO_LLR skips the LLR array too -- 80 instead of 321 MB come back per train at C3. */
+  CCO_FLAG_RESULT_NO_COUNT = 16,
+  CCO_FLAG_RESULT_NO_LLR = 32
 };
 
 /*
@@ -102,6 +117,11 @@ typedef struct {
   /* world_size > 1: 128-byte NCCL unique id obtained from cco_nccl_unique_id() on rank 0 and
    * distributed by the host (any transport); ignored when world_size == 1 */
   const unsigned char *nccl_unique_id;
+  /* optional (NULL / 0 = library-owned pinned memory): host memory the result arrays are placed in, e.g. a shared
+   * segment another process maps, so that this rank's indicator slice reaches its reader without a copy.  The library
+   * page-locks it (cudaHostRegister) for the life of the context; it is reused once every result has been freed. */
+  void *result_arena;
+  size_t result_arena_bytes;
 } cco_config_t;
 
 typedef struct cco_ctx cco_ctx_t;
@@ -139,6 +159,14 @@ int cco_device_count(void);
 int cco_nccl_unique_id(unsigned char out[128]);
 
 int cco_create(const cco_config_t *cfg, cco_ctx_t **out);
+/*
+ * Group context: ONE context over several B200s of this process -- what the single Spark-driver thread of the reference
+ * (URAlgorithm.scala:292-307) can drive through JNI.  cco_train / cco_cooccurrences_idss on it run one host thread per
+ * GPU inside the library (NCCL communicator from ncclCommInitAll): each GPU uploads its block of user rows from the SAME
+ * host matrices, computes a work-balanced range of primary-item rows, and copies its slice into ONE merged result (full
+ * row range, one set of host arrays).  Resident datasets (cco_dataset_upload / cco_ingest) stay per-GPU APIs.
+ */
+int cco_create_group(int32_t n_devices, const int32_t *devices, cco_ctx_t **out);
 int cco_destroy(cco_ctx_t *ctx);
 
 /* Pinned host memory the caller can fill directly (e.g. wrapped as a direct ByteBuffer by the

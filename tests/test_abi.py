@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(_native.LIB_PATH)
     for name in declared_symbols():
         assert hasattr(lib, name), f"{name} declared in include/cco_b200.h but not exported"
-    assert lib.cco_abi_version() == 1
+    assert lib.cco_abi_version() == 2
 
 
 def test_status_strings():

@@ -9,8 +9,8 @@ Host-side mirror of the reference interface for this path:
   SimilarityAnalysis.cooccurrencesIDSs / crossOccurrenceDownsampled  <- URAlgorithm.scala:323,343
   ur_algorithm.calc_all                   <- URAlgorithm.calcAll          (URAlgorithm.scala:310-349)
 """
-from ._native import (CcoError, CcoInvalidArgument, FLAG_ASSUME_CANONICAL, FLAG_ENTROPY_VARARGS,
-                      FLAG_ROWRATE_INTDIV, LIB_PATH)
+from ._native import (CcoError, CcoInvalidArgument, FLAG_ASSUME_CANONICAL, FLAG_ENTROPY_VARARGS, FLAG_RESULT_NO_COUNT,
+                      FLAG_RESULT_NO_LLR, FLAG_ROWRATE_INTDIV, LIB_PATH)
 from .indexed_dataset import BiDictionary, IndexedDataset
 from .preparator import prepare
 from .similarity_analysis import (CcoContext, DownsamplableCrossOccurrenceDataset, SimilarityAnalysis,
@@ -21,5 +21,5 @@ __all__ = [
     "BiDictionary", "CcoContext", "CcoError", "CcoInvalidArgument", "DefaultURAlgoParams",
     "DownsamplableCrossOccurrenceDataset", "IndexedDataset", "IndicatorParams", "SimilarityAnalysis",
     "URAlgorithmParams", "calc_all", "default_context", "prepare", "FLAG_ASSUME_CANONICAL",
-    "FLAG_ENTROPY_VARARGS", "FLAG_ROWRATE_INTDIV", "LIB_PATH",
+    "FLAG_ENTROPY_VARARGS", "FLAG_ROWRATE_INTDIV", "FLAG_RESULT_NO_COUNT", "FLAG_RESULT_NO_LLR", "LIB_PATH",
 ]

@@ -16,6 +16,8 @@ FLAG_ROWRATE_INTDIV = 1
 FLAG_ENTROPY_VARARGS = 2
 FLAG_ASSUME_CANONICAL = 4
 FLAG_RESULT_ON_DEVICE = 8
+FLAG_RESULT_NO_COUNT = 16
+FLAG_RESULT_NO_LLR = 32
 MAX_TOP_K = 2048
 
 
@@ -43,7 +45,7 @@ class ParamsT(C.Structure):
 
 class ConfigT(C.Structure):
     _fields_ = [("device", C.c_int32), ("rank", C.c_int32), ("world_size", C.c_int32), ("reserved", C.c_int32),
-                ("nccl_unique_id", C.POINTER(C.c_ubyte))]
+                ("nccl_unique_id", C.POINTER(C.c_ubyte)), ("result_arena", C.c_void_p), ("result_arena_bytes", C.c_size_t)]
 
 
 class EventsT(C.Structure):
@@ -67,7 +69,7 @@ class StatsT(C.Structure):
 # every symbol include/cco_b200.h declares (tests/test_abi.py checks the export table against this)
 EXPORTS = [
     "cco_abi_version", "cco_last_error", "cco_status_string", "cco_device_count", "cco_nccl_unique_id",
-    "cco_create", "cco_destroy", "cco_host_alloc", "cco_host_free", "cco_train", "cco_cooccurrences_idss",
+    "cco_create", "cco_create_group", "cco_destroy", "cco_host_alloc", "cco_host_free", "cco_train", "cco_cooccurrences_idss",
     "cco_dataset_upload", "cco_train_dataset", "cco_dataset_free", "cco_timer_start", "cco_timer_stop",
     "cco_partition_rows", "cco_ingest", "cco_synth_ingest", "cco_dataset_shape", "cco_dataset_download",
     "cco_dataset_copy_to_host",
@@ -95,6 +97,7 @@ def lib():
     L.cco_device_count.restype = C.c_int
     L.cco_nccl_unique_id.argtypes = [p(C.c_ubyte)]
     L.cco_create.argtypes = [p(ConfigT), p(C.c_void_p)]
+    L.cco_create_group.argtypes = [C.c_int32, p(C.c_int32), p(C.c_void_p)]
     L.cco_destroy.argtypes = [C.c_void_p]
     L.cco_host_alloc.argtypes = [C.c_void_p, C.c_size_t, p(C.c_void_p)]
     L.cco_host_free.argtypes = [C.c_void_p, C.c_void_p]

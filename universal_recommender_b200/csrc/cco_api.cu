@@ -163,10 +163,10 @@ struct cco_ctx {
   std::vector<cco_ctx *> members;
   GroupShared *gshared = nullptr;   // set on members
 
-  void *pinned_get(size_t bytes) {
+  void *pinned_get(size_t bytes, bool for_result = true) {
     std::lock_guard<std::mutex> lk(mu);
     if (bytes == 0) bytes = 16;
-    if (arena) {
+    if (arena && for_result) {
       const size_t off = (arena_used + 255) & ~(size_t)255;
       if (off + bytes <= arena_bytes) {
         arena_used = off + bytes;
@@ -1325,21 +1325,53 @@ int cco_nccl_unique_id(unsigned char out[128]) {
   return CCO_OK;
 }
 
-int cco_create(const cco_config_t *cfg, cco_ctx_t **out) {
-  if (!cfg || !out) return set_error(CCO_E_INVALID_ARG, "null argument");
-  if (cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size)
-    return set_error(CCO_E_INVALID_ARG, "bad rank/world_size %d/%d", cfg->rank, cfg->world_size);
+// streams, events, mailbox, memory pool of one per-GPU context (the NCCL communicator is attached by the caller)
+static int ctx_init_device(cco_ctx *c) {
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  for (auto &ev : c->ev) CK(cudaEventCreate(&ev));
+  for (auto &ev : c->tev) CK(cudaEventCreate(&ev));
+  for (auto &ev : c->copy_ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  for (auto &st : c->bin_stream) CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  for (auto &ev : c->bin_ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  CK(cudaHostAlloc((void **)&c->mail_h, kMailBytes, cudaHostAllocMapped | cudaHostAllocPortable));
+  CK(cudaHostGetDevicePointer((void **)&c->mail_d, c->mail_h, 0));
+  cudaMemPool_t pool;
+  CK(cudaDeviceGetDefaultMemPool(&pool, c->device));
+  uint64_t thr = UINT64_MAX;  // keep freed blocks: steady-state trains allocate nothing
+  CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  return CCO_OK;
+}
+
+static int check_device(int device, cudaDeviceProp *p) {
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess || n == 0)
     return set_error(CCO_E_CUDA, "no CUDA device (%s): this library has no CPU fallback",
                      e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
-  if (cfg->device < 0 || cfg->device >= n) return set_error(CCO_E_INVALID_ARG, "device %d not in [0,%d)", cfg->device, n);
+  if (device < 0 || device >= n) return set_error(CCO_E_INVALID_ARG, "device %d not in [0,%d)", device, n);
+  CK(cudaGetDeviceProperties(p, device));
+  if (p->major != 10)
+    return set_error(CCO_E_CUDA, "device %d is sm_%d%d; this build contains sm_100a code only", device, p->major, p->minor);
+  return CCO_OK;
+}
+
+static int create_failed(cco_ctx *c, int st) {
+  char keep[sizeof g_err];
+  memcpy(keep, g_err, sizeof keep);   // cco_destroy must not clobber the message
+  cco_destroy(c);
+  memcpy(g_err, keep, sizeof keep);
+  return st;
+}
+
+int cco_create(const cco_config_t *cfg, cco_ctx_t **out) {
+  if (!cfg || !out) return set_error(CCO_E_INVALID_ARG, "null argument");
+  if (cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size)
+    return set_error(CCO_E_INVALID_ARG, "bad rank/world_size %d/%d", cfg->rank, cfg->world_size);
+  if (cfg->world_size > 1023) return set_error(CCO_E_UNSUPPORTED, "world_size %d > 1023", cfg->world_size);
   cudaDeviceProp p;
-  CK(cudaGetDeviceProperties(&p, cfg->device));
-  if (p.major != 10)
-    return set_error(CCO_E_CUDA, "device %d is sm_%d%d; this build contains sm_100a code only", cfg->device, p.major, p.minor);
-  CK(cudaSetDevice(cfg->device));
+  CKR(check_device(cfg->device, &p));
   if (cfg->world_size > 1 && !cfg->nccl_unique_id) return set_error(CCO_E_INVALID_ARG, "world_size > 1 needs nccl_unique_id");
   cco_ctx *c = new cco_ctx();
   c->device = cfg->device;
@@ -1349,19 +1381,15 @@ int cco_create(const cco_config_t *cfg, cco_ctx_t **out) {
   c->smem_optin = p.sharedMemPerBlockOptin;
   // every failure below releases what was created so far (cco_destroy tolerates a half-built context)
   auto init = [&]() -> int {
-    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    for (auto &ev : c->ev) CK(cudaEventCreate(&ev));
-    for (auto &ev : c->tev) CK(cudaEventCreate(&ev));
-    for (auto &ev : c->copy_ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    for (auto &st : c->bin_stream) CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    for (auto &ev : c->bin_ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    CK(cudaHostAlloc((void **)&c->mail_h, kMailBytes, cudaHostAllocMapped));
-    CK(cudaHostGetDevicePointer((void **)&c->mail_d, c->mail_h, 0));
-    cudaMemPool_t pool;
-    CK(cudaDeviceGetDefaultMemPool(&pool, cfg->device));
-    uint64_t thr = UINT64_MAX;  // keep freed blocks: steady-state trains allocate nothing
-    CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    CKR(ctx_init_device(c));
+    if (cfg->result_arena && cfg->result_arena_bytes > 0) {
+      // caller-provided result memory (e.g. a shared-memory segment the reading process maps): page-lock it so the
+      // device->host copies of the indicators land there directly
+      CK(cudaHostRegister(cfg->result_arena, cfg->result_arena_bytes, cudaHostRegisterPortable));
+      c->arena = (unsigned char *)cfg->result_arena;
+      c->arena_bytes = cfg->result_arena_bytes;
+      c->arena_registered = true;
+    }
     if (c->world > 1) {
       CKR(load_nccl());
       ncclUniqueId id;
@@ -1372,25 +1400,78 @@ int cco_create(const cco_config_t *cfg, cco_ctx_t **out) {
     return CCO_OK;
   };
   const int st = init();
-  if (st != CCO_OK) {
-    char keep[sizeof g_err];
-    memcpy(keep, g_err, sizeof keep);   // cco_destroy must not clobber the message
-    cco_destroy(c);
-    memcpy(g_err, keep, sizeof keep);
-    return st;
-  }
+  if (st != CCO_OK) return create_failed(c, st);
   *out = c;
+  return CCO_OK;
+}
+
+// One context over several GPUs of this process (what a single JVM thread can drive): member r runs on devices[r] with
+// its own streams; the communicator comes from ncclCommInitAll; cco_train runs one host thread per member.
+int cco_create_group(int32_t n_devices, const int32_t *devices, cco_ctx_t **out) {
+  if (!devices || !out || n_devices < 1) return set_error(CCO_E_INVALID_ARG, "bad argument");
+  if (n_devices > 1023) return set_error(CCO_E_UNSUPPORTED, "more than 1023 devices");
+  std::vector<cudaDeviceProp> props(n_devices);
+  for (int r = 0; r < n_devices; ++r) {
+    CKR(check_device(devices[r], &props[r]));
+    for (int q = 0; q < r; ++q)
+      if (devices[q] == devices[r]) return set_error(CCO_E_INVALID_ARG, "device %d listed twice", devices[r]);
+  }
+  cco_ctx *leader = new cco_ctx();
+  leader->device = devices[0];
+  leader->world = 1;
+  GroupShared *gs = new GroupShared();
+  gs->world = n_devices;
+  auto init = [&]() -> int {
+    std::vector<ncclComm_t> comms(n_devices, nullptr);
+    if (n_devices > 1) {
+      CKR(load_nccl());
+      std::vector<int> devs(devices, devices + n_devices);
+      int rc = g_nccl.CommInitAll(comms.data(), n_devices, devs.data());
+      if (rc != 0) return set_error(CCO_E_NCCL, "ncclCommInitAll: %s", g_nccl.GetErrorString(rc));
+    }
+    for (int r = 0; r < n_devices; ++r) {
+      cco_ctx *m = new cco_ctx();
+      m->device = devices[r];
+      m->rank = r;
+      m->world = n_devices;
+      m->sm_count = props[r].multiProcessorCount;
+      m->smem_optin = props[r].sharedMemPerBlockOptin;
+      m->comm = comms[r];
+      m->gshared = gs;
+      leader->members.push_back(m);
+      CKR(ctx_init_device(m));
+    }
+    CK(cudaSetDevice(devices[0]));
+    return CCO_OK;
+  };
+  const int st = init();
+  if (st != CCO_OK) {
+    if (leader->members.empty()) delete gs;
+    return create_failed(leader, st);
+  }
+  *out = leader;
   return CCO_OK;
 }
 
 int cco_destroy(cco_ctx_t *c) {
   if (!c) return CCO_OK;
+  if (!c->members.empty()) {
+    GroupShared *gs = c->members[0]->gshared;
+    for (cco_ctx *m : c->members) {
+      m->gshared = nullptr;
+      cco_destroy(m);
+    }
+    c->members.clear();
+    delete gs;
+  }
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
   if (c->comm) g_nccl.CommDestroy(c->comm);
   for (auto &b : c->pinned) cudaFreeHost(b.p);
+  if (c->arena_registered) cudaHostUnregister(c->arena);
   if (c->mail_h) cudaFreeHost(c->mail_h);
+  for (auto &ev : c->mail_ev) cudaEventDestroy(ev);
   for (auto &ev : c->ev)
     if (ev) cudaEventDestroy(ev);
   for (auto &ev : c->tev)
@@ -1410,7 +1491,7 @@ int cco_destroy(cco_ctx_t *c) {
 int cco_host_alloc(cco_ctx_t *c, size_t bytes, void **out) {
   if (!c || !out) return set_error(CCO_E_INVALID_ARG, "null argument");
   CK(cudaSetDevice(c->device));
-  void *p = c->pinned_get(bytes);
+  void *p = c->pinned_get(bytes, /*for_result=*/false);
   if (!p) return set_error(CCO_E_OOM, "cudaHostAlloc(%zu) failed", bytes);
   *out = p;
   return CCO_OK;
@@ -1425,6 +1506,8 @@ int cco_train(cco_ctx_t *ctx, int32_t n_mats, const cco_csr_t *mats, const cco_i
               uint32_t flags, cco_result_t **out) {
   if (!ctx || !out) return set_error(CCO_E_INVALID_ARG, "null argument");
   *out = nullptr;
+  CKR(validate_host(n_mats, mats, params));   // everything the host can check, before any GPU (or thread) starts
+  if (!ctx->members.empty()) return train_group(ctx, n_mats, mats, params, seed, flags, out);
   return train_impl(ctx, n_mats, mats, params, seed, flags, out);
 }
 
@@ -1766,6 +1849,7 @@ int cco_partition_rows(const int64_t *work_prefix, int32_t n_items, int32_t worl
 
 int cco_dataset_upload(cco_ctx_t *ctx, int32_t n_mats, const cco_csr_t *mats, uint32_t flags, cco_dataset_t **out) {
   if (!ctx || !out) return set_error(CCO_E_INVALID_ARG, "null argument");
+  if (!ctx->members.empty()) return set_error(CCO_E_UNSUPPORTED, "resident datasets are per GPU: use cco_train on a group context");
   *out = nullptr;
   std::vector<cco_indicator_params_t> p(std::max(n_mats, 1), cco_indicator_params_t{1, 1, 0, 0.0});
   CKR(validate_host(n_mats, mats, p.data()));

@@ -46,11 +46,28 @@ class CcoContext:
     """One GPU context (= cco_ctx_t).  One process per GPU; for world_size > 1 pass the 128-byte NCCL id
     from `CcoContext.nccl_unique_id()` of rank 0 (distribute it with any host transport)."""
 
-    def __init__(self, device: int = 0, rank: int = 0, world_size: int = 1, nccl_unique_id: bytes | None = None):
+    def __init__(self, device: int = 0, rank: int = 0, world_size: int = 1, nccl_unique_id: bytes | None = None,
+                 devices: Sequence[int] | None = None, result_arena: np.ndarray | None = None):
+        """devices=[...]: a GROUP context over several GPUs of this process (cco_create_group): train_csr then returns the
+        merged model of all of them.  result_arena: a writable uint8 array (e.g. np.memmap of a /dev/shm file) the result
+        arrays are placed in (cco_config_t.result_arena)."""
         L = N.lib()
         self._L = L
         self._uid = None
-        cfg = N.ConfigT(device, rank, world_size, 0, None)
+        self._arena = result_arena
+        self.last_stats: TrainStats | None = None
+        self._pinned_addr: dict = {}
+        if devices is not None:
+            h = C.c_void_p()
+            arr = (C.c_int32 * len(devices))(*devices)
+            N.check(L.cco_create_group(len(devices), arr, C.byref(h)))
+            self._h = h
+            self.rank, self.world_size, self.device, self.devices = 0, 1, devices[0], list(devices)
+            return
+        cfg = N.ConfigT(device, rank, world_size, 0, None, None, 0)
+        if result_arena is not None:
+            cfg.result_arena = result_arena.ctypes.data
+            cfg.result_arena_bytes = result_arena.nbytes
         if world_size > 1:
             if nccl_unique_id is None or len(nccl_unique_id) != 128:
                 raise N.CcoInvalidArgument(N.E_INVALID_ARG, "world_size > 1 needs the 128-byte nccl_unique_id")
@@ -59,9 +76,7 @@ class CcoContext:
         h = C.c_void_p()
         N.check(L.cco_create(C.byref(cfg), C.byref(h)))
         self._h = h
-        self.rank, self.world_size, self.device = rank, world_size, device
-        self.last_stats: TrainStats | None = None
-        self._pinned_addr: dict = {}
+        self.rank, self.world_size, self.device, self.devices = rank, world_size, device, [device]
 
     @staticmethod
     def nccl_unique_id() -> bytes:
