@@ -214,13 +214,19 @@ def workload_desc(name: str) -> str:
 class ShmModel:
     """N > 1 end-to-end leg: the caller of the reference boundary is ONE process (URAlgorithm.train on the Spark driver,
     URAlgorithm.scala:292-307), so the model is only "back" when every rank's row slice sits in memory that process can
-    read.  Each rank copies its slice into its own region of one /dev/shm segment; after the barrier rank 0 holds views of
-    all of them (a row-partitioned model: exactly what toStringMapRDD iterates over)."""
+    read.  One /dev/shm segment holds a region per rank; the region (minus a 4 KB header) is that rank's RESULT ARENA
+    (cco_config_t.result_arena): the library page-locks it and the device->host copies of the indicators land in it
+    directly.  After the train a rank only publishes where its arrays are; rank 0 reads every slice in place."""
+
+    HEAD = 4096
 
     def __init__(self, rank: int, world: int, n_types: int, n_items: int, top_k: int, tag: str):
         self.rank, self.world, self.n_types = rank, world, n_types
-        self.per_ind = 8 * (n_items + 1) + 16 * n_items * top_k + 64
-        self.per_rank = 4096 + n_types * self.per_ind
+        per_ind = 8 * (n_items + 1) + 16 * n_items * top_k + 4096
+        # a rank holds ~1/world of the rows (work-balanced): three times that share, at least 64 MB; a result that still
+        # does not fit is allocated by the library outside the arena and publish() says so
+        share = n_types * per_ind if world <= 2 else 3 * n_types * per_ind // world
+        self.per_rank = (self.HEAD + max(share, 64 << 20) + (1 << 21) - 1) & ~((1 << 21) - 1)
         self.path = f"/dev/shm/cco_bench_model_{tag}"
         if rank == 0:
             with open(self.path, "wb") as f:
@@ -229,19 +235,18 @@ class ShmModel:
 
     def open(self):
         self.mm = np.memmap(self.path, dtype=np.uint8, mode="r+")
+        return self.mm[self.rank * self.per_rank + self.HEAD:(self.rank + 1) * self.per_rank]   # this rank's arena
 
     def publish(self, res):
-        """copy this rank's slices (views of the library's pinned result buffers) into the shared segment"""
+        """res: views of this rank's result arrays (they live in the arena): record their offsets in the header"""
         base = self.rank * self.per_rank
-        head = np.zeros(4 * self.n_types, dtype=np.int64)
-        off = base + 4096
+        addr0 = self.mm.ctypes.data
+        head = np.zeros(8 * self.n_types, dtype=np.int64)
         for i, (rb, re_, nc, rp, ci, ll, cn) in enumerate(res):
             nnz = int(rp[-1])
-            head[4 * i:4 * i + 4] = (rb, re_, nnz, off)
-            for arr in (rp, ci, ll):
-                b = arr.view(np.uint8)
-                self.mm[off:off + b.size] = b
-                off += (b.size + 63) & ~63
+            offs = [a.ctypes.data - addr0 if a.size else 0 for a in (rp, ci, ll, cn)]
+            assert all(o == 0 or base <= o < base + self.per_rank for o in offs), "result outside the arena"
+            head[8 * i:8 * i + 8] = (rb, re_, nnz, offs[0], offs[1], offs[2], offs[3], nc)
         self.mm[base:base + head.nbytes] = head.view(np.uint8)
 
     def model(self):
@@ -249,16 +254,15 @@ class ShmModel:
         out = []
         for r in range(self.world):
             base = r * self.per_rank
-            head = self.mm[base:base + 32 * self.n_types].view(np.int64)
+            head = self.mm[base:base + 64 * self.n_types].view(np.int64)
             sl = []
             for i in range(self.n_types):
-                rb, re_, nnz, off = (int(x) for x in head[4 * i:4 * i + 4])
-                rp = self.mm[off:off + 8 * (re_ - rb + 1)].view(np.int64)
-                off += (8 * (re_ - rb + 1) + 63) & ~63
-                ci = self.mm[off:off + 4 * nnz].view(np.int32)
-                off += (4 * nnz + 63) & ~63
-                ll = self.mm[off:off + 8 * nnz].view(np.float64)
-                sl.append((rb, re_, rp, ci, ll))
+                rb, re_, nnz, o_rp, o_ci, o_ll, o_cn, nc = (int(x) for x in head[8 * i:8 * i + 8])
+                rp = self.mm[o_rp:o_rp + 8 * (re_ - rb + 1)].view(np.int64)
+                ci = self.mm[o_ci:o_ci + 4 * nnz].view(np.int32)
+                ll = self.mm[o_ll:o_ll + 8 * nnz].view(np.float64) if o_ll else np.zeros(0, np.float64)
+                cn = self.mm[o_cn:o_cn + 4 * nnz].view(np.int32) if o_cn else np.zeros(0, np.int32)
+                sl.append((rb, re_, rp, ci, ll, cn, nc))
             out.append(sl)
         return out
 
@@ -327,7 +331,13 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    ctx = ur.CcoContext(device=local_rank, rank=rank, world_size=world, nccl_unique_id=uid)
+    shm, arena = None, None
+    if world > 1:
+        c = synth.CONFIGS[args.workload]
+        shm = ShmModel(rank, world, c["n_types"], c["n_items"], 50, os.environ.get("MASTER_PORT", "0"))
+        barrier()
+        arena = shm.open()
+    ctx = ur.CcoContext(device=local_rank, rank=rank, world_size=world, nccl_unique_id=uid, result_arena=arena)
     # synthetic events are generated and ingested on the device (cco_synth_ingest; every rank builds the same matrices on
     # its own GPU) and copied into pinned host memory: what the JNI shim's direct ByteBuffers would hold
     t_gen = time.perf_counter()
@@ -366,14 +376,12 @@ def main():
 
     # ---- end to end through cco_train with host buffers ------------------------------------------------------
     # N > 1: the timed region ends when rank 0 can read the WHOLE model (every rank's row slice) from host memory
-    shm = None
-    if world > 1:
-        shm = ShmModel(rank, world, w.n_types, n_items_a, w.top_k, os.environ.get("MASTER_PORT", "0"))
-        barrier()
-        shm.open()
+    # the indicator matrices of the reference boundary are (column id, LLR) per row (IndexedDataset values = LLR); the
+    # co-occurrence count k11 is a by-product nothing downstream reads, so the end-to-end leg does not copy it back
+    flags_e2e = flags | N.FLAG_RESULT_NO_COUNT
 
     def e2e_step():
-        res, h = ctx.train_csr(pinned, w.params, args.seed, flags, keep=True)
+        res, h = ctx.train_csr(pinned, w.params, args.seed, flags_e2e, keep=True)
         nbytes = sum(r[3].nbytes + r[4].nbytes + r[5].nbytes + r[6].nbytes for r in res)
         if shm is not None:
             shm.publish(res)
@@ -381,6 +389,8 @@ def main():
             if rank == 0:
                 model = shm.model()
                 assert sum(sl[0][1] - sl[0][0] for sl in model) == n_items_a
+                assert all(int(sl[i][2][-1]) == len(sl[i][3]) for sl in model for i in range(w.n_types))
+            dist.barrier()          # the slices are read in place: nobody frees before rank 0 is done
         ctx.free_result(h)
         return nbytes
 
@@ -405,16 +415,20 @@ def main():
     else:
         sw, sdesc = sample_workload(args.workload, sample, ctx, pinned=True)
         spinned = sw.mats
-    local = ctx.train_csr(spinned, sw.params, args.seed, flags)
     parity = None
-    merged = local
-    if world > 1:
-        box = [None] * world if rank == 0 else None
-        dist.gather_object(local, box, dst=0)
+    if world == 1:
+        merged = ctx.train_csr(spinned, sw.params, args.seed, flags)
+        ph = None
+    else:
+        # every rank's slice sits in its result arena (= its region of the shared segment): rank 0 merges them in place
+        local, ph = ctx.train_csr(spinned, sw.params, args.seed, flags, keep=True)
+        shm.publish(local)
+        dist.barrier()
         if rank == 0:
+            model = shm.model()
             merged = []
             for i in range(sw.n_types):
-                m = D.merge_row_slices([box[r][i] for r in range(world)])    # (n_rows, n_cols, row_ptr, col, llr, count)
+                m = D.merge_row_slices([(sl[i][0], sl[i][1], sl[i][6], sl[i][2], sl[i][3], sl[i][4], sl[i][5]) for sl in model])
                 merged.append((0, m[0], m[1], m[2], m[3], m[4], m[5]))
     if rank == 0:
         from oracle import oracle as orc
@@ -423,6 +437,9 @@ def main():
         parity = par.compare(ref, merged, sw.n_users)
         parity["sample"] = sdesc
         parity["n_gpus"] = world
+    if world > 1:
+        dist.barrier()
+        ctx.free_result(ph)
 
     # ---- roofline of the fused A'^T B' row kernel (all ranks' rows together) -----------------------------------
     peak, peak_src = measured_peaks()
@@ -449,12 +466,14 @@ def main():
                        if h2d_bytes > 126e6 else "inputs fit L2 (%.0f MB); no explicit flush" % (h2d_bytes / 1e6),
                        "resident": "value: matrices resident in HBM, indicators left packed in HBM",
                        "e2e": "cco_train on pinned host CSR -> indicator arrays in host memory" +
-                              (" of rank 0 (every rank's row slice published to one shared segment inside the timed region)" if world > 1 else ""),
+                              (" readable by rank 0 (every rank's result arena is its region of one shared segment; the merge is "
+                               "zero-copy and inside the timed region)" if world > 1 else ""),
                        "products_per_step": int(sum_over_ranks(float(sum(st_last.products)))),
                        "distinct_cells_per_step": int(sum_over_ranks(float(sum(st_last.distinct_cells)))),
                        "datagen_s": round(t_gen, 1), "build": source_build_id(),
                        "stage_ms_last_resident_step": {"prepare": round(st_last.ms_prepare, 3), "indicators_total": round(st_last.ms_cooccurrence, 3),
-                                                       "row_kernels": [round(x, 3) for x in st_last.ms_indicator]}},
+                                                       "row_kernels": [round(x, 3) for x in st_last.ms_indicator],
+                                                       "prepare_stages": [round(x, 3) for x in (st_last.ms_prep_stage or [])[:7]]}},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": d2h_total,
                     "ms_per_step": ms_e2e},

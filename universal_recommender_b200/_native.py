@@ -63,7 +63,7 @@ class StatsT(C.Structure):
                 ("distinct_cells", C.c_int64 * 16), ("out_nnz", C.c_int64 * 16), ("llr_evaluated", C.c_int64 * 16),
                 ("ms_h2d", C.c_float), ("ms_prepare", C.c_float), ("ms_cooccurrence", C.c_float),
                 ("ms_d2h", C.c_float), ("ms_total", C.c_float), ("ms_indicator", C.c_float * 16),
-                ("n_kernel_launches", C.c_int32), ("n_mats", C.c_int32)]
+                ("n_kernel_launches", C.c_int32), ("n_mats", C.c_int32), ("ms_prep_stage", C.c_float * 8)]
 
 
 # every symbol include/cco_b200.h declares (tests/test_abi.py checks the export table against this)

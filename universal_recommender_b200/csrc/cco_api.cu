@@ -218,6 +218,7 @@ struct cco_dataset {
   std::vector<int32_t *> col;    // device, indexable by the values of rp
   std::vector<void *> rp_alloc, col_alloc;   // what to free (rp/col may be offset views of these)
   std::vector<long long> block_cap;          // per matrix: largest raw entry count of any rank's user block
+  std::vector<long long> q_lo, q_hi;         // per matrix: the offsets rp[0], rp[n_local] of the block (host-known)
   std::vector<cudaEvent_t> ready;  // per matrix: host->device copy finished (copy stream)
   bool h2d_pending = false;        // uploaded asynchronously: ms_h2d is read when the train joins
   bool validated = false;          // k_check_rows has run (and the rows are canonical)
@@ -395,8 +396,69 @@ static int canonicalize_device(cco_ctx *c, Arena &ar, DevRaw &m) {
   return CCO_OK;
 }
 
+// rows with more than kHeavyRow entries of a block, listed once per train and matrix (k_list_heavy_rows)
+struct HeavyRows {
+  int32_t *list = nullptr;
+  int *n = nullptr;
+};
+static int list_heavy_rows(cco_ctx *c, Arena &ar, const DevRaw &raw, HeavyRows *h) {
+  CKR(ar.alloc(&h->list, std::max<long long>(raw.n_rows, 1)));
+  CKR(ar.alloc(&h->n, 1));
+  CK(cudaMemsetAsync(h->n, 0, 4, c->stream));
+  if (raw.n_rows > 0) {
+    k_list_heavy_rows<<<grid_for(raw.n_rows, 256, c->sm_count), 256, 0, c->stream>>>(raw.n_rows, raw.rp, h->list, h->n);
+    c->launches++;
+  }
+  return CCO_OK;
+}
+// a row-parallel pass = one launch over the light rows (kSG lanes per row) + one over the listed heavy rows (a warp per
+// row; a fixed few waves of CTAs loop over the list, whose length they read on the device)
+static void launch_check(cco_ctx *c, const DevRaw &raw, const HeavyRows &h, int *flags) {
+  if (raw.n_rows <= 0) return;
+  const long long q_lo = raw.q_base, q_hi = raw.q_base + raw.nnz;
+  k_check_rows<kSG><<<grid_for(raw.n_rows * kSG, 256, c->sm_count), 256, 0, c->stream>>>(raw.n_rows, raw.n_cols, raw.rp, raw.col, q_lo, q_hi,
+                                                                                       nullptr, nullptr, flags);
+  k_check_rows<32><<<c->sm_count * 4, 256, 0, c->stream>>>(raw.n_rows, raw.n_cols, raw.rp, raw.col, q_lo, q_hi, h.list, h.n, flags);
+  c->launches += 2;
+}
+// per-matrix scratch of the two sampling passes: integer keep thresholds per column, one keep byte per stored entry
+struct SampleScratch {
+  unsigned long long *col_thr = nullptr;
+  uint8_t *keep = nullptr;
+};
+static int sample_scratch(cco_ctx *c, Arena &ar, const DevRaw &raw, const int32_t *raw_counts, int32_t m, SampleScratch *sc) {
+  CKR(ar.alloc(&sc->col_thr, std::max<int32_t>(raw.n_cols, 1)));
+  CKR(ar.alloc(&sc->keep, std::max<long long>(raw.nnz, 1)));
+  if (raw.n_cols > 0) {
+    k_col_thresholds<<<grid_for(raw.n_cols, 256, c->sm_count, 4), 256, 0, c->stream>>>(raw.n_cols, raw_counts, m, sc->col_thr);
+    c->launches++;
+  }
+  return CCO_OK;
+}
+static void launch_count(cco_ctx *c, const DevRaw &raw, const HeavyRows &h, const SampleScratch &sc, int32_t m, int32_t seed,
+                         uint32_t flags, uint32_t *kept, int32_t *new_counts) {
+  if (raw.n_rows <= 0) return;
+  const long long q_lo = raw.q_base, q_hi = raw.q_base + raw.nnz;
+  k_downsample_count<kSG><<<grid_for(raw.n_rows * kSG, 256, c->sm_count), 256, 0, c->stream>>>(raw.n_rows, raw.row_base, raw.rp, raw.col, raw.n_cols,
+                                                                                             q_lo, q_hi, sc.col_thr, m, seed, flags, nullptr, nullptr,
+                                                                                             kept, new_counts, sc.keep);
+  k_downsample_count<32><<<c->sm_count * 4, 256, 0, c->stream>>>(raw.n_rows, raw.row_base, raw.rp, raw.col, raw.n_cols, q_lo, q_hi, sc.col_thr, m,
+                                                                 seed, flags, h.list, h.n, kept, new_counts, sc.keep);
+  c->launches += 2;
+}
+static void launch_write(cco_ctx *c, const DevRaw &raw, const HeavyRows &h, const SampleScratch &sc, const uint32_t *new_ptr,
+                         const uint32_t *out_base, int32_t *new_col) {
+  if (raw.n_rows <= 0) return;
+  const long long q_lo = raw.q_base, q_hi = raw.q_base + raw.nnz;
+  k_downsample_write<kSG><<<grid_for(raw.n_rows * kSG, 256, c->sm_count), 256, 0, c->stream>>>(raw.n_rows, raw.row_base, raw.rp, raw.col, q_lo, q_hi,
+                                                                                             sc.keep, nullptr, nullptr, new_ptr, out_base, new_col);
+  k_downsample_write<32><<<c->sm_count * 4, 256, 0, c->stream>>>(raw.n_rows, raw.row_base, raw.rp, raw.col, q_lo, q_hi, sc.keep, h.list, h.n,
+                                                                 new_ptr, out_base, new_col);
+  c->launches += 2;
+}
+
 // sampleDownAndBinarize of one whole matrix on this GPU (raw column counts already final in raw_counts)
-static int downsample_device(cco_ctx *c, Arena &ar, const DevRaw &raw, const int32_t *raw_counts, int32_t m,
+static int downsample_device(cco_ctx *c, Arena &ar, const DevRaw &raw, const HeavyRows &heavy, const int32_t *raw_counts, int32_t m,
                              int32_t seed, uint32_t flags, DevMat *out) {
   out->n_rows = raw.n_rows;
   out->n_cols = raw.n_cols;
@@ -407,13 +469,15 @@ static int downsample_device(cco_ctx *c, Arena &ar, const DevRaw &raw, const int
   CKR(ar.alloc(&out->col, std::max<long long>(raw.nnz, 1)));
   CK(cudaMemsetAsync(out->marg, 0, sizeof(int32_t) * std::max<int32_t>(raw.n_cols, 1), c->stream));
   CK(cudaMemsetAsync(kept + raw.n_rows, 0, 4, c->stream));
-  int g = grid_for(raw.n_rows * kSG, 256, c->sm_count);
-  k_downsample_count<<<g, 256, 0, c->stream>>>(raw.n_rows, 0, raw.rp, raw.col, raw_counts, m, seed, flags, kept, out->marg);
+  SampleScratch sc;
+  CKR(sample_scratch(c, ar, raw, raw_counts, m, &sc));
+  launch_count(c, raw, heavy, sc, m, seed, flags, kept, out->marg);
   CKR(exclusive_sum_u32(c, ar, kept, out->rp, raw.n_rows + 1));
-  k_downsample_write<<<g, 256, 0, c->stream>>>(raw.n_rows, 0, raw.rp, raw.col, raw_counts, m, seed, flags, out->rp, nullptr, out->col);
-  c->launches += 2;
+  launch_write(c, raw, heavy, sc, out->rp, nullptr, out->col);
   CK(cudaGetLastError());
   ar.release(kept);
+  ar.release(sc.col_thr);
+  ar.release(sc.keep);
   return CCO_OK;
 }
 
@@ -429,15 +493,17 @@ static int nccl_check(int rc, const char *what) {
 //   (3) all-reduce of the post-sample column counts             -> marginals (nothing is re-counted on the gathered matrix)
 //   (4) all-gather of the sampled column blocks, each padded to the largest raw block (a size the host knows from the
 //       caller's row_ptr), then a pack kernel that reads the true block lengths from row_ptr on the device.
-static int downsample_sharded_all(cco_ctx *c, Arena &ar, const std::vector<DevRaw> &raw, const std::vector<long long> &block_cap,
+static int downsample_sharded_all(cco_ctx *c, Arena &ar, const std::vector<DevRaw> &raw, const std::vector<HeavyRows> &heavy,
+                                  const std::vector<long long> &block_cap,
                                   long long U, const int32_t *raw_counts, int32_t *marg_all, const std::vector<long long> &col_off,
-                                  const cco_indicator_params_t *params, int32_t seed, uint32_t flags, std::vector<DevMat> &dm) {
+                                  const cco_indicator_params_t *params, int32_t seed, uint32_t flags, std::vector<DevMat> &dm,
+                                  cudaEvent_t *stage_ev /* [4]: after pass 1, after collectives + scans, after pass 2, after gather + pack */) {
   cudaStream_t s = c->stream;
   const int W = c->world, r = c->rank, n_mats = (int)raw.size();
   const long long S = (U + W - 1) / W;
-  const long long n_local = raw[0].n_rows, row_base = raw[0].row_base;
-  const int g = grid_for(std::max<long long>(n_local, 1) * kSG, 256, c->sm_count);
+  const long long row_base = raw[0].row_base;
   std::vector<uint32_t *> kept(n_mats, nullptr);
+  std::vector<SampleScratch> sc(n_mats);
   for (int i = 0; i < n_mats; ++i) {
     DevMat *out = &dm[i];
     out->n_rows = U;
@@ -446,12 +512,10 @@ static int downsample_sharded_all(cco_ctx *c, Arena &ar, const std::vector<DevRa
     CKR(ar.alloc(&kept[i], (size_t)(W * S + 1)));
     CKR(ar.alloc(&out->rp, U + 1));
     CK(cudaMemsetAsync(kept[i], 0, sizeof(uint32_t) * (size_t)(W * S + 1), s));
-    if (n_local > 0) {
-      k_downsample_count<<<g, 256, 0, s>>>(n_local, row_base, raw[i].rp, raw[i].col, raw_counts + col_off[i], params[i].max_interactions,
-                                           seed, flags, kept[i], out->marg);
-      c->launches++;
-    }
+    CKR(sample_scratch(c, ar, raw[i], raw_counts + col_off[i], params[i].max_interactions, &sc[i]));
+    launch_count(c, raw[i], heavy[i], sc[i], params[i].max_interactions, seed, flags, kept[i], out->marg);
   }
+  CK(cudaEventRecord(stage_ev[0], s));
   if (S > 0) {
     g_nccl.GroupStart();
     for (int i = 0; i < n_mats; ++i) {
@@ -466,17 +530,19 @@ static int downsample_sharded_all(cco_ctx *c, Arena &ar, const std::vector<DevRa
   for (int i = 0; i < n_mats; ++i) {
     CKR(exclusive_sum_u32(c, ar, kept[i], dm[i].rp, U + 1));
     ar.release(kept[i]);
+  }
+  CK(cudaEventRecord(stage_ev[1], s));
+  for (int i = 0; i < n_mats; ++i) {
     const long long cap = block_cap[i];
     CKR(ar.alloc(&dm[i].col, std::max<long long>(raw[i].nnz_cap, 1)));
     if (cap == 0) continue;
     CKR(ar.alloc(&gathered[i], (size_t)(cap * W)));
-    if (n_local > 0) {
-      // this rank's block goes straight into its slot of the gather buffer, relative to the block's first entry
-      k_downsample_write<<<g, 256, 0, s>>>(n_local, row_base, raw[i].rp, raw[i].col, raw_counts + col_off[i], params[i].max_interactions,
-                                           seed, flags, dm[i].rp, dm[i].rp + row_base, gathered[i] + (size_t)r * cap);
-      c->launches++;
-    }
+    // this rank's block goes straight into its slot of the gather buffer, relative to the block's first entry
+    launch_write(c, raw[i], heavy[i], sc[i], dm[i].rp, dm[i].rp + row_base, gathered[i] + (size_t)r * cap);
+    ar.release(sc[i].col_thr);
+    ar.release(sc[i].keep);
   }
+  CK(cudaEventRecord(stage_ev[2], s));
   g_nccl.GroupStart();
   for (int i = 0; i < n_mats; ++i) {
     if (!gathered[i]) continue;
@@ -491,6 +557,7 @@ static int downsample_sharded_all(cco_ctx *c, Arena &ar, const std::vector<DevRa
     c->launches++;
     ar.release(gathered[i]);
   }
+  CK(cudaEventRecord(stage_ev[3], s));
   CK(cudaGetLastError());
   return CCO_OK;
 }
@@ -921,9 +988,16 @@ static int dataset_validate(cco_ctx *c, cco_dataset *d, bool canonicalise) {
   for (int i = 0; i < n_mats; ++i) {
     CK(cudaStreamWaitEvent(s, d->ready[i], 0));
     if (d->n_local == 0) continue;
-    k_check_rows<<<grid_for(d->n_local * kSG, 256, c->sm_count), 256, 0, s>>>(d->n_local, (int32_t)d->n_cols[i], d->rp[i], d->col[i],
-                                                                          d_flags + 2 * i);
-    c->launches++;
+    DevRaw r;
+    r.n_rows = d->n_local;
+    r.n_cols = (int32_t)d->n_cols[i];
+    r.q_base = d->q_lo[i];
+    r.nnz = d->q_hi[i] - d->q_lo[i];
+    r.rp = d->rp[i];
+    r.col = d->col[i];
+    HeavyRows hv;
+    CKR(list_heavy_rows(c, ar, r, &hv));
+    launch_check(c, r, hv, d_flags + 2 * i);
   }
   if (c->world > 1)
     CKR(nccl_check(g_nccl.AllReduce(d_flags, d_flags, (size_t)(2 * n_mats), kNcclInt32, kNcclMax, c->comm, s), "ncclAllReduce(check flags)"));
@@ -941,16 +1015,14 @@ static int dataset_validate(cco_ctx *c, cco_dataset *d, bool canonicalise) {
         r.n_rows = d->n_local;
         r.row_base = d->row_base;
         r.n_cols = (int32_t)d->n_cols[i];
-        long long q0 = 0, q1 = 0;
-        CK(cudaMemcpyAsync(&q0, d->rp[i], 8, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(&q1, d->rp[i] + d->n_local, 8, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        r.q_base = q0;
-        r.nnz = q1 - q0;
+        r.q_base = d->q_lo[i];
+        r.nnz = d->q_hi[i] - d->q_lo[i];
         r.rp = d->rp[i];
         r.col = d->col[i];
         CKR(canonicalize_device(c, ar, r));
         d->col[i] = r.col;
+        d->q_lo[i] = 0;
+        d->q_hi[i] = r.nnz;
         if (c->world == 1) d->nnz[i] = r.nnz;
       }
   CK(cudaStreamSynchronize(s));
@@ -978,6 +1050,8 @@ static int dataset_upload(cco_ctx *c, int32_t n_mats, const cco_csr_t *mats, uin
   d->n_cols.assign(n_mats, 0);
   d->nnz.assign(n_mats, 0);
   d->block_cap.assign(n_mats, 0);
+  d->q_lo.assign(n_mats, 0);
+  d->q_hi.assign(n_mats, 0);
   d->ready.assign(n_mats, nullptr);
   struct G {
     cco_dataset *d;
@@ -999,6 +1073,8 @@ static int dataset_upload(cco_ctx *c, int32_t n_mats, const cco_csr_t *mats, uin
       d->block_cap[i] = std::max<long long>(d->block_cap[i], m.row_ptr[a1] - m.row_ptr[a0]);
     }
     const long long q0 = m.row_ptr[u_lo], q1 = m.row_ptr[u_hi];
+    d->q_lo[i] = q0;
+    d->q_hi[i] = q1;
     void *p = nullptr;
     cudaError_t e = cudaMallocAsync(&p, sizeof(int64_t) * ((size_t)d->n_local + 1), s);
     if (e != cudaSuccess) return set_error(CCO_E_OOM, "cudaMallocAsync row_ptr: %s", cudaGetErrorString(e));
@@ -1079,7 +1155,8 @@ static int train_dataset(cco_ctx *c, const cco_dataset *ds, const cco_indicator_
     raw[i].n_rows = ds->n_local;
     raw[i].row_base = ds->row_base;
     raw[i].n_cols = (int32_t)ds->n_cols[i];
-    raw[i].nnz = ds->nnz[i];   // bound: the block never holds more than the whole matrix
+    raw[i].q_base = ds->q_lo[i];
+    raw[i].nnz = ds->q_hi[i] - ds->q_lo[i];   // entries of the block
     raw[i].nnz_cap = ds->nnz[i];
     raw[i].rp = ds->rp[i];
     raw[i].col = ds->col[i];
@@ -1087,6 +1164,12 @@ static int train_dataset(cco_ctx *c, const cco_dataset *ds, const cco_indicator_
   }
   CK(cudaEventRecord(c->ev[1], s));
   nvtx_push("cco:prepare");
+  std::vector<cudaEvent_t> sev(8, nullptr);   // stage boundaries of the preparation (cco_stats_t.ms_prep_stage)
+  for (auto &e : sev) {
+    CK(cudaEventCreate(&e));
+    evg.extra.push_back(e);
+  }
+  auto mark = [&](int k) { return cudaEventRecord(sev[k], s); };
   // raw column counts: this rank histograms its user block; ONE allreduce sums all matrices' counts
   long long total_cols = 0;
   std::vector<long long> col_off(n_mats + 1, 0);
@@ -1105,16 +1188,17 @@ static int train_dataset(cco_ctx *c, const cco_dataset *ds, const cco_indicator_
   CK(cudaMemsetAsync(raw_counts, 0, sizeof(int32_t) * (size_t)copy_stride * kHistCopies, s));
   CK(cudaMemsetAsync(marg_all, 0, sizeof(int32_t) * (size_t)copy_stride, s));
   CK(cudaMemsetAsync(d_check, 0, sizeof(int) * 2 * n_mats, s));
+  std::vector<HeavyRows> heavy(n_mats);
   for (int i = 0; i < n_mats; ++i) {
     CK(cudaStreamWaitEvent(s, ds->ready[i], 0));  // matrix i has landed (async upload: later ones may still be in flight)
     if (ds->n_local == 0) continue;
+    CKR(list_heavy_rows(c, ar, raw[i], &heavy[i]));
     if (!ds->validated) {
       // CCO_FLAG_ASSUME_CANONICAL skips the canonicalisation, not the safety net: a malformed matrix still fails the call
-      k_check_rows<<<grid_for(ds->n_local * kSG, 256, c->sm_count), 256, 0, s>>>(ds->n_local, raw[i].n_cols, raw[i].rp, raw[i].col,
-                                                                             d_check + 2 * i);
-      c->launches++;
+      // (until the verdict is read the passes below skip whatever points outside the block or the column space)
+      launch_check(c, raw[i], heavy[i], d_check + 2 * i);
     }
-    k_col_histogram<<<grid_for(raw[i].nnz / c->world + 1, 256, c->sm_count), 256, 0, s>>>(0, ds->n_local, raw[i].rp, raw[i].col,
+    k_col_histogram<<<grid_for(raw[i].nnz + 1, 256, c->sm_count), 256, 0, s>>>(0, ds->n_local, raw[i].rp, raw[i].col, raw[i].n_cols,
                                                                                        raw_counts + col_off[i], kHistCopies, copy_stride);
     c->launches++;
   }
@@ -1122,20 +1206,26 @@ static int train_dataset(cco_ctx *c, const cco_dataset *ds, const cco_indicator_
     k_sum_copies<<<grid_for(total_cols, 256, c->sm_count), 256, 0, s>>>(total_cols, kHistCopies, copy_stride, raw_counts);
     c->launches++;
   }
+  CK(mark(0));
   if (c->world > 1) {
     if (total_cols > 0)
       CKR(nccl_check(g_nccl.AllReduce(raw_counts, raw_counts, (size_t)total_cols, kNcclInt32, kNcclSum, c->comm, s), "ncclAllReduce(raw counts)"));
     CKR(nccl_check(g_nccl.AllReduce(d_check, d_check, (size_t)(2 * n_mats), kNcclInt32, kNcclMax, c->comm, s), "ncclAllReduce(check flags)"));
   }
+  CK(mark(1));
   // sampleDownAndBinarize every matrix
   std::vector<DevMat> dm(n_mats);
   if (c->world > 1) {
-    CKR(downsample_sharded_all(c, ar, raw, ds->block_cap, n_users, raw_counts, marg_all, col_off, params, seed, flags, dm));
+    CKR(downsample_sharded_all(c, ar, raw, heavy, ds->block_cap, n_users, raw_counts, marg_all, col_off, params, seed, flags, dm, &sev[2]));
   } else {
     for (int i = 0; i < n_mats; ++i) {
       dm[i].marg = marg_all + col_off[i];
-      CKR(downsample_device(c, ar, raw[i], raw_counts + col_off[i], params[i].max_interactions, seed, flags, &dm[i]));
+      CKR(downsample_device(c, ar, raw[i], heavy[i], raw_counts + col_off[i], params[i].max_interactions, seed, flags, &dm[i]));
     }
+    CK(mark(2));   // single GPU: both passes are booked on stage 2 ... 4 as one block
+    CK(mark(3));
+    CK(mark(4));
+    CK(mark(5));
   }
   // `drmA.t`
   const int32_t n_items_a = dm[0].n_cols;
@@ -1168,6 +1258,7 @@ static int train_dataset(cco_ctx *c, const cco_dataset *ds, const cco_indicator_
   CKR(mail_fetch(c, max_marg.data(), d_max, 4 * (size_t)n_mats));
   CKR(mail_fetch(c, h_check.data(), d_check, sizeof(int) * 2 * (size_t)n_mats));
   for (int i = 0; i < n_mats; ++i) CKR(mail_fetch(c, &h_nnz[i], dm[i].rp + n_users, 4));
+  CK(mark(6));
   CK(cudaEventRecord(c->ev[2], s));
   nvtx_pop();
   CKR(mail_wait(c));   // the one host round trip of the preparation: the packed-word check needs the largest marginals
@@ -1203,6 +1294,8 @@ static int train_dataset(cco_ctx *c, const cco_dataset *ds, const cco_indicator_
     CK(cudaEventElapsedTime(&st.ms_indicator[i], ev_rows[2 * i], ev_rows[2 * i + 1]));
   }
   if (h2d_pending) CK(cudaEventElapsedTime(&st.ms_h2d, c->ev[6], c->ev[7]));
+  CK(cudaEventElapsedTime(&st.ms_prep_stage[0], c->ev[1], sev[0]));
+  for (int k = 1; k <= 6; ++k) CK(cudaEventElapsedTime(&st.ms_prep_stage[k], sev[k - 1], sev[k]));
   CK(cudaEventElapsedTime(&st.ms_prepare, c->ev[1], c->ev[2]));
   CK(cudaEventElapsedTime(&st.ms_cooccurrence, c->ev[2], c->ev[3]));
   CK(cudaEventElapsedTime(&st.ms_total, c->ev[1], c->ev[3]));
@@ -1581,6 +1674,8 @@ static int ingest_core(cco_ctx *c, const IngestSource &src, int32_t min_events_p
   d->rp_alloc.assign(n_types, nullptr);
   d->col_alloc.assign(n_types, nullptr);
   d->block_cap.assign(n_types, 0);
+  d->q_lo.assign(n_types, 0);
+  d->q_hi.assign(n_types, 0);
   d->n_cols.assign(n_types, 0);
   d->nnz.assign(n_types, 0);
   d->ready.assign(n_types, nullptr);
@@ -1723,6 +1818,8 @@ static int ingest_core(cco_ctx *c, const IngestSource &src, int32_t min_events_p
   CKR(mail_wait(c));
   for (int t = 0; t < n_types; ++t) {
     for (int q = 0; q < c->world; ++q) d->block_cap[t] = std::max(d->block_cap[t], edge[t][q + 1] - edge[t][q]);
+    d->q_lo[t] = edge[t][c->rank];
+    d->q_hi[t] = edge[t][c->rank + 1];
     d->rp[t] += u_lo;   // views of the block; rp_alloc / col_alloc keep the whole matrices
   }
   CK(cudaStreamSynchronize(s));
@@ -1972,9 +2069,11 @@ int cco_debug_downsample(cco_ctx_t *c, const cco_csr_t *m, int32_t max_interacti
   CKR(ar.alloc(&counts, std::max<int32_t>(m->n_cols, 1)));
   CK(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)std::max<int32_t>(m->n_cols, 1), c->stream));
   if (raw.nnz > 0 && m->n_rows > 0)
-    k_col_histogram<<<grid_for(raw.nnz, 256, c->sm_count), 256, 0, c->stream>>>(0, m->n_rows, raw.rp, raw.col, counts, 1, 0);
+    k_col_histogram<<<grid_for(raw.nnz, 256, c->sm_count), 256, 0, c->stream>>>(0, m->n_rows, raw.rp, raw.col, raw.n_cols, counts, 1, 0);
   DevMat dm;
-  CKR(downsample_device(c, ar, raw, counts, max_interactions, seed, flags, &dm));
+  HeavyRows hv;
+  CKR(list_heavy_rows(c, ar, raw, &hv));
+  CKR(downsample_device(c, ar, raw, hv, counts, max_interactions, seed, flags, &dm));
   std::vector<uint32_t> rp32((size_t)m->n_rows + 1);
   CK(cudaMemcpyAsync(rp32.data(), dm.rp, sizeof(uint32_t) * rp32.size(), cudaMemcpyDeviceToHost, c->stream));
   if (raw_col_counts && m->n_cols > 0)
@@ -2024,8 +2123,10 @@ int cco_debug_cooccurrence(cco_ctx_t *c, const cco_csr_t *a, const cco_csr_t *b,
     CKR(ar.alloc(&counts, std::max<int32_t>(raw[i].n_cols, 1)));
     CK(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)std::max<int32_t>(raw[i].n_cols, 1), s));
     if (raw[i].nnz > 0 && raw[i].n_rows > 0)
-      k_col_histogram<<<grid_for(raw[i].nnz, 256, c->sm_count), 256, 0, s>>>(0, raw[i].n_rows, raw[i].rp, raw[i].col, counts, 1, 0);
-    CKR(downsample_device(c, ar, raw[i], counts, 0x7fffffff, 0, 0, &dm[i]));
+      k_col_histogram<<<grid_for(raw[i].nnz, 256, c->sm_count), 256, 0, s>>>(0, raw[i].n_rows, raw[i].rp, raw[i].col, raw[i].n_cols, counts, 1, 0);
+    HeavyRows hv;
+    CKR(list_heavy_rows(c, ar, raw[i], &hv));
+    CKR(downsample_device(c, ar, raw[i], hv, counts, 0x7fffffff, 0, 0, &dm[i]));
   }
   const int32_t n_items_a = dm[0].n_cols;
   uint32_t *at_ptr, *cursor, *marg_pad;

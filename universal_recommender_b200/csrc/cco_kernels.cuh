@@ -146,22 +146,40 @@ __global__ void k_debug_llr(long long n, const long long *k11, const long long *
 // ------------------------------------------------------------------------------------------------
 constexpr int kSG = 8;  // lanes per user row in the preparation passes (avg row ~10-30 entries)
 
-// flags[0] |= malformed (row_ptr not monotone / column out of range), flags[1] |= not canonical
-__global__ void k_check_rows(long long n_rows, int32_t n_cols, const long long *__restrict__ rp,
-                             const int32_t *__restrict__ col, int *flags) {
-  const int lane = threadIdx.x % kSG;
-  long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / kSG;
-  const long long stride = (long long)gridDim.x * blockDim.x / kSG;
+// Row-parallel passes give a row to a sub-group of kSG lanes.  A user with thousands of entries would keep one sub-group
+// busy long after the rest of the grid has drained (Zipf users: the top row of C3 has ~6 K entries, of C4 ~40 K) -- and
+// that tail does not shrink when the users are sharded over GPUs.  Rows above kHeavyRow entries are therefore listed once
+// (k_list_heavy_rows) and handled by a second launch of the same kernel with a whole warp per listed row.
+constexpr int kHeavyRow = 256;
+__global__ void k_list_heavy_rows(long long n_rows, const long long *__restrict__ rp, int32_t *__restrict__ list, int *__restrict__ n_list) {
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n_rows; r += (long long)gridDim.x * blockDim.x)
+    if (rp[r + 1] - rp[r] > kHeavyRow) list[atomicAdd(n_list, 1)] = (int32_t)r;
+}
+// the rows one launch walks: every light row (list == nullptr) or the listed heavy ones
+#define CCO_ROW_LOOP_BEGIN(SG)                                                                         \
+  const int lane = threadIdx.x % SG;                                                                   \
+  long long it = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / SG;                              \
+  const long long stride = (long long)gridDim.x * blockDim.x / SG;                                     \
+  const long long n_it = list ? (long long)*n_list : n_rows;                                           \
+  for (; it < n_it; it += stride) {                                                                    \
+    const long long row = list ? (long long)list[it] : it;
+#define CCO_ROW_LOOP_END }
+
+// flags[0] |= malformed (row_ptr not monotone / outside [q_lo, q_hi] / column out of range), flags[1] |= not canonical
+template <int SG>
+__global__ void k_check_rows(long long n_rows, int32_t n_cols, const long long *__restrict__ rp, const int32_t *__restrict__ col,
+                             long long q_lo, long long q_hi, const int32_t *__restrict__ list, const int *__restrict__ n_list, int *flags) {
   int bad = 0, unsorted = 0;
-  for (; row < n_rows; row += stride) {
+  CCO_ROW_LOOP_BEGIN(SG)
     long long s = rp[row], e = rp[row + 1];
-    if (e < s) { bad = 1; continue; }
-    for (long long q = s + lane; q < e; q += kSG) {
+    if (e < s || s < q_lo || e > q_hi) { bad = 1; continue; }   // never dereference an offset outside the uploaded block
+    if (!list && e - s > kHeavyRow) continue;
+    for (long long q = s + lane; q < e; q += SG) {
       int32_t c = col[q];
       if (c < 0 || c >= n_cols) bad = 1;
       if (q > s && col[q - 1] >= c) unsorted = 1;
     }
-  }
+  CCO_ROW_LOOP_END
   if (bad) atomicOr(&flags[0], 1);
   if (unsorted) atomicOr(&flags[1], 1);
 }
@@ -171,7 +189,7 @@ __global__ void k_check_rows(long long n_rows, int32_t n_cols, const long long *
 // entries hit one column, and its atomics serialise in one L2 slice (~0.3 ms per 12.5 M-entry matrix at C3);
 // k_sum_copies folds the copies back into copy 0.
 __global__ void k_col_histogram(long long row_begin, long long row_end, const long long *__restrict__ rp,
-                                const int32_t *__restrict__ col, int32_t *__restrict__ counts, int n_copies,
+                                const int32_t *__restrict__ col, int32_t n_cols, int32_t *__restrict__ counts, int n_copies,
                                 long long copy_stride) {
   // element-parallel over the contiguous slice rp[row_begin]..rp[row_end]; warp-uniform trip count
   const long long s = rp[row_begin], e = rp[row_end];
@@ -186,7 +204,8 @@ __global__ void k_col_histogram(long long row_begin, long long row_end, const lo
       int32_t c = col[q];
       // warp-aggregate lanes hitting the same column (Zipf-hot columns)
       unsigned peers = __match_any_sync(am, c);
-      if ((__ffs(peers) - 1) == lane) atomicAdd(&mine[c], __popc(peers));
+      // (an out-of-range id of a not yet validated matrix is skipped here and reported by k_check_rows)
+      if ((__ffs(peers) - 1) == lane && (uint32_t)c < (uint32_t)n_cols) atomicAdd(&mine[c], __popc(peers));
     }
   }
 }
@@ -221,79 +240,94 @@ __device__ __forceinline__ double row_sample_rate(long long d, int32_t m, bool i
   const long long md = d < m ? d : (long long)m;
   return intdiv ? (double)(md / d) : __ddiv_rn((double)md, (double)d);
 }
-// keep (row, j)?  Bit-identical to oracle/cco_oracle.c orc_downsample: the sample rate is exactly 1.0 whenever the
-// row and the column are within m (x/x == 1.0 in IEEE), and u01 < 1, so those entries skip the hash and the division.
-__device__ __forceinline__ bool keep_entry(long long d, double row_rate, int32_t c, int32_t m, int32_t seed, uint32_t row,
-                                           uint32_t j) {
-  if (d <= m && c <= m) return true;
-  const double col_rate = c <= m ? 1.0 : __ddiv_rn((double)m, (double)c);
-  const double rate = row_rate < col_rate ? row_rate : col_rate;
-  return sample_u01(seed, row, j) <= rate;
+// The sampler keeps (u, j) iff u01 <= min(rowRate, colRate) with u01 = (h >> 11) * 2^-53 (include/cco_b200.h "Sampler";
+// bit-identical to oracle/cco_oracle.c orc_downsample).  u01 is a 53-bit integer scaled by a power of two, so the
+// comparison is exactly  (h >> 11) <= floor(rate * 2^53): rates become integer thresholds -- one per column (k_col_thresholds,
+// once per train) and one per row -- and an entry costs one mix64 and one integer compare, no fp64 division.  A rate of
+// 1 (row and column within m) gets the threshold 2^53: u01 < 1 always passes, the hash is not even computed.
+constexpr unsigned long long kKeepAlways = 1ULL << 53;
+__device__ __forceinline__ unsigned long long rate_threshold(double rate) {
+  if (rate >= 1.0) return kKeepAlways;
+  return (unsigned long long)floor(__dmul_rn(rate, 0x1.0p53));   // exact: a power-of-two scaling, then the integer part
+}
+__global__ void k_col_thresholds(int32_t n_cols, const int32_t *__restrict__ raw_counts, int32_t m, unsigned long long *__restrict__ thr) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_cols; j += gridDim.x * blockDim.x) {
+    const int32_t c = raw_counts[j];
+    thr[j] = c <= m ? kKeepAlways : rate_threshold(__ddiv_rn((double)m, (double)c));
+  }
+}
+__device__ __forceinline__ bool keep_entry_thr(unsigned long long t_row, unsigned long long t_col, uint64_t x_row, uint32_t j) {
+  const unsigned long long t = t_row < t_col ? t_row : t_col;
+  if (t >= kKeepAlways) return true;
+  const uint64_t h = mix64(x_row + (uint64_t)j * 0x9e3779b97f4a7c15ULL);
+  return (h >> 11) <= t;
 }
 
 // pass 1 of sampleDownAndBinarize: kept entries per row + post-sample column marginals.
-// The matrix handed in is a block of n_local user rows (the whole matrix on one GPU, this rank's user block otherwise);
+// The matrix handed in is a block of n_rows user rows (the whole matrix on one GPU, this rank's user block otherwise);
 // row_base = global index of its first user: the sampler hashes GLOBAL user ids and kept_per_row is indexed globally.
-__global__ void k_downsample_count(long long n_local, long long row_base, const long long *__restrict__ rp, const int32_t *__restrict__ col,
-                                   const int32_t *__restrict__ raw_counts, int32_t m, int32_t seed, uint32_t flags,
-                                   uint32_t *__restrict__ kept_per_row, int32_t *__restrict__ new_counts) {
-  const int lane = threadIdx.x % kSG;
-  const unsigned sg_mask = ((1u << kSG) - 1u) << ((threadIdx.x & 31) / kSG * kSG);
-  long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / kSG;
-  const long long stride = (long long)gridDim.x * blockDim.x / kSG;
+template <int SG>
+__global__ void k_downsample_count(long long n_rows, long long row_base, const long long *__restrict__ rp, const int32_t *__restrict__ col,
+                                   int32_t n_cols, long long q_lo, long long q_hi, const unsigned long long *__restrict__ col_thr, int32_t m,
+                                   int32_t seed, uint32_t flags, const int32_t *__restrict__ list, const int *__restrict__ n_list,
+                                   uint32_t *__restrict__ kept_per_row, int32_t *__restrict__ new_counts, uint8_t *__restrict__ keep_flag) {
+  const unsigned sg_mask = SG == 32 ? 0xffffffffu : (((1u << SG) - 1u) << ((threadIdx.x & 31) / SG * SG));
   const bool intdiv = (flags & CCO_FLAG_ROWRATE_INTDIV) != 0;
   // all lanes of a sub-group share `row`, so loop trip counts are sub-group uniform
-  for (; row < n_local; row += stride) {
+  CCO_ROW_LOOP_BEGIN(SG)
     long long s = rp[row], e = rp[row + 1], d = e - s;
-    const double row_rate = row_sample_rate(d, m, intdiv);
+    if (!list && d > kHeavyRow) continue;
+    if (d < 0 || s < q_lo || e > q_hi) continue;   // malformed row_ptr: k_check_rows reports it
+    const unsigned long long t_row = rate_threshold(row_sample_rate(d, m, intdiv));
     const uint32_t g = (uint32_t)(row_base + row);
+    const uint64_t x_row = mix64(((uint64_t)(uint32_t)seed << 32) | (uint64_t)g);
     uint32_t kept = 0;
-    for (long long q0 = s; q0 < e; q0 += kSG) {
+    for (long long q0 = s; q0 < e; q0 += SG) {
       long long q = q0 + lane;
       bool keep = false;
       int32_t j = 0;
       if (q < e) {
         j = col[q];
-        keep = keep_entry(d, row_rate, raw_counts[j], m, seed, g, (uint32_t)j);
+        // (ids outside [0, n_cols) belong to a malformed matrix: dropped here, reported by k_check_rows)
+        keep = (uint32_t)j < (uint32_t)n_cols && keep_entry_thr(t_row, col_thr[j], x_row, (uint32_t)j);
+        keep_flag[q - q_lo] = keep ? 1 : 0;   // pass 2 compacts by these decisions instead of hashing again
       }
       if (keep && new_counts) atomicAdd(&new_counts[j], 1);
       kept += __popc(__ballot_sync(sg_mask, keep) & sg_mask);
     }
     if (lane == 0) kept_per_row[g] = kept;
-  }
+  CCO_ROW_LOOP_END
 }
 
-// pass 2: ordered compaction (ascending columns are preserved).  new_ptr is the GLOBAL row pointer of the sampled
-// matrix; out_base (nullable) points at the entry the output buffer starts at (this rank's block offset when the block is
-// written into a send buffer, null = 0 when it is written in place).
-__global__ void k_downsample_write(long long n_local, long long row_base, const long long *__restrict__ rp, const int32_t *__restrict__ col,
-                                   const int32_t *__restrict__ raw_counts, int32_t m, int32_t seed, uint32_t flags,
+// pass 2: ordered compaction by the recorded decisions (ascending columns are preserved).  new_ptr is the GLOBAL row
+// pointer of the sampled matrix; out_base (nullable) points at the entry the output buffer starts at (this rank's block
+// offset when the block is written into a send buffer, null = 0 when it is written in place).
+template <int SG>
+__global__ void k_downsample_write(long long n_rows, long long row_base, const long long *__restrict__ rp, const int32_t *__restrict__ col,
+                                   long long q_lo, long long q_hi, const uint8_t *__restrict__ keep_flag,
+                                   const int32_t *__restrict__ list, const int *__restrict__ n_list,
                                    const uint32_t *__restrict__ new_ptr, const uint32_t *__restrict__ out_base, int32_t *__restrict__ new_col) {
-  const int lane = threadIdx.x % kSG;
-  const int sg_shift = (threadIdx.x & 31) / kSG * kSG;
-  const unsigned sg_mask = ((1u << kSG) - 1u) << sg_shift;
-  long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / kSG;
-  const long long stride = (long long)gridDim.x * blockDim.x / kSG;
-  const bool intdiv = (flags & CCO_FLAG_ROWRATE_INTDIV) != 0;
+  const int sg_shift = SG == 32 ? 0 : (threadIdx.x & 31) / SG * SG;
+  const unsigned sg_mask = SG == 32 ? 0xffffffffu : (((1u << SG) - 1u) << sg_shift);
   const uint32_t base = out_base ? *out_base : 0u;
-  for (; row < n_local; row += stride) {
+  CCO_ROW_LOOP_BEGIN(SG)
     long long s = rp[row], e = rp[row + 1], d = e - s;
-    const double row_rate = row_sample_rate(d, m, intdiv);
-    const uint32_t g = (uint32_t)(row_base + row);
-    uint32_t w = new_ptr[g] - base;
-    for (long long q0 = s; q0 < e; q0 += kSG) {
+    if (!list && d > kHeavyRow) continue;
+    if (d < 0 || s < q_lo || e > q_hi) continue;
+    uint32_t w = new_ptr[row_base + row] - base;
+    for (long long q0 = s; q0 < e; q0 += SG) {
       long long q = q0 + lane;
       bool keep = false;
       int32_t j = 0;
       if (q < e) {
         j = col[q];
-        keep = keep_entry(d, row_rate, raw_counts[j], m, seed, g, (uint32_t)j);
+        keep = keep_flag[q - q_lo] != 0;
       }
       unsigned b = (__ballot_sync(sg_mask, keep) & sg_mask) >> sg_shift;
       if (keep) new_col[w + __popc(b & ((1u << lane) - 1u))] = j;
       w += __popc(b);
     }
-  }
+  CCO_ROW_LOOP_END
 }
 
 // multi-GPU: every rank sampled its user block into a padded send buffer; after the all-gather the W padded blocks

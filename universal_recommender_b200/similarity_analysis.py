@@ -40,6 +40,7 @@ class TrainStats:
     ms_total: float
     ms_indicator: list
     n_kernel_launches: int
+    ms_prep_stage: list = None
 
 
 class CcoContext:
@@ -162,7 +163,7 @@ class CcoContext:
             N.check(L.cco_result_stats(res, C.byref(st)))
             self.last_stats = TrainStats(st.n_users, st.nnz_in_total, list(st.nnz_downsampled)[:n], list(st.products)[:n],
                                          list(st.distinct_cells)[:n], list(st.out_nnz)[:n], list(st.llr_evaluated)[:n], st.ms_h2d, st.ms_prepare,
-                                         st.ms_cooccurrence, st.ms_total, list(st.ms_indicator)[:n], st.n_kernel_launches)
+                                         st.ms_cooccurrence, st.ms_total, list(st.ms_indicator)[:n], st.n_kernel_launches, list(st.ms_prep_stage))
             if keep:
                 h, res = res, None
                 return out, h
