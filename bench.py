@@ -276,10 +276,11 @@ class ShmModel:
 
 
 def source_build_id() -> str:
-    """hash of the kernel sources: a committed ncu traffic figure is only quoted for the build it was measured on"""
+    """hash of the kernel source (cco_kernels.cuh holds k_rows and every preparation kernel): a committed ncu traffic
+    figure is only quoted for the kernels it was measured on"""
     import hashlib
     h = hashlib.sha1()
-    for f in ("cco_api.cu", "cco_kernels.cuh"):
+    for f in ("cco_kernels.cuh",):
         try:
             h.update(open(os.path.join(ROOT, "universal_recommender_b200", "csrc", f), "rb").read())
         except OSError:

@@ -274,6 +274,38 @@ int cco_result_stats(const cco_result_t *r, cco_stats_t *out);
 int cco_result_free(cco_result_t *r);
 
 /*
+ * Next row: the model as the Elasticsearch bulk body, assembled on the device.  Replaces, per primary item,
+ * IndexedDatasetConversions.toStringMapRDD (src/main/scala/package.scala:82-110: non-zeros ordered by -LLR, mapped to
+ * column id strings, LLR dropped, empty rows -> empty array), URModel.save's groupAll + ("id" -> item)
+ * (src/main/scala/URModel.scala:47-102) and the bulk serialisation of saveToEs with es.mapping.id = id
+ * (src/main/scala/EsClient.scala:300-313).  One document per row of the result (a rank's slice or a merged model):
+ *     {"index":{"_id":"<item>"}}\n{"id":"<item>","<names[0]>":["<col>",...],"<names[1]>":[...]}\n
+ * Strings are JSON-escaped here ('"' and '\\' get a backslash, bytes < 0x20 become \u00xx, the rest passes through).
+ * dictionaries: id i = bytes[offsets[i] .. offsets[i + 1]) (UTF-8); row_ids covers the primary item space, col_ids[i]
+ * the item space of event i.  *out_bytes is pinned memory owned by the context: release it with cco_host_free.
+ */
+typedef struct {
+  int64_t n;
+  const int64_t *offsets; /* [n + 1] */
+  const char *bytes;
+} cco_dictionary_t;
+int cco_format_es_bulk(cco_ctx_t *ctx, const cco_result_t *res, int32_t n_names, const char *const *names,
+                       const cco_dictionary_t *row_ids, const cco_dictionary_t *col_ids, char **out_bytes, int64_t *out_len);
+
+/*
+ * Next row: the backfill ranks of PopModel (src/main/scala/PopModel.scala:113-182) as per-item event
+ * histograms over 1 / 2 / 3 time buckets of [start_ms, end_ms) -- what URAlgorithm.getRanksRDD (URAlgorithm.scala:537-560)
+ * joins into the model.  events: (item index, event time in epoch milliseconds), already restricted to the ranking's event
+ * names.  score[j] is meaningful iff present[j] != 0: `popular` lists the items with an event in the interval, `trending`
+ * the items seen in both halves (newer - older), `hot` the items seen in all three thirds ((newer - middle) - (middle -
+ * older)); `trending` / `hot` are empty when the older (or middle) bucket has no event at all, as in the reference.
+ * RankingType.Random / UserDefined are not histograms and stay with the caller.
+ */
+enum { CCO_POP_POPULAR = 0, CCO_POP_TRENDING = 1, CCO_POP_HOT = 2 };
+int cco_pop_model(cco_ctx_t *ctx, int32_t mode, int64_t n_events, const int32_t *item, const int64_t *time_ms, int32_t n_items,
+                  int64_t start_ms, int64_t end_ms, double *score, unsigned char *present);
+
+/*
  * Debug/parity entry (tests only): full integer co-occurrence matrix A^T B of two canonical
  * binary matrices computed by the same accumulation kernel as cco_train, no LLR, no top-k.
  * Output CSR over the columns of A with ascending column ids, malloc'ed; free with cco_free.

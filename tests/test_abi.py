@@ -48,15 +48,18 @@ def test_no_cpu_fallback_without_gpu():
 
 
 def test_product_package_never_imports_the_oracle():
-    """Only tests/, __graft_entry__.smoke() and bench.py may touch oracle/."""
+    """Only tests/, __graft_entry__.smoke() and bench.py may touch oracle/.  Python files of the package must not mention
+    it at all; CUDA sources may name the restatement they are checked against in comments, nothing else."""
     pkg = os.path.join(ROOT, "universal_recommender_b200")
     for dirpath, _, files in os.walk(pkg):
         for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h")):
-                txt = open(os.path.join(dirpath, f)).read()
-                assert "oracle" not in txt.lower() or f in ("cco_kernels.cuh",), f"{f} mentions the oracle"
-    k = open(os.path.join(pkg, "csrc", "cco_kernels.cuh")).read()
-    assert "#include" not in "".join(l for l in k.splitlines() if "oracle" in l.lower())
+            txt = open(os.path.join(dirpath, f), errors="replace").read() if f.endswith((".py", ".cu", ".cuh", ".h")) else ""
+            if f.endswith(".py"):
+                assert "oracle" not in txt.lower(), f"{f} mentions the oracle"
+            elif txt:
+                for line in txt.splitlines():
+                    if "oracle" in line.lower():
+                        assert line.lstrip().startswith(("//", "*", "/*")) and "#include" not in line, f"{f}: {line.strip()}"
 
 
 def test_plain_c_program_links_against_the_abi(tmp_path):

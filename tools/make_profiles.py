@@ -65,12 +65,16 @@ for row in r[2:]:
               f"{g('sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active'):.0f} | {g('smsp__inst_executed.sum') / 1e6:.0f} | {row[col('launch__registers_per_thread')]} | "
               f"{s('barrier')} / {s('wait')} / {s('long_scoreboard')} / {s('short_scoreboard')} / {s('branch_resolving')} |")
     tr += g("dram__bytes_read.sum"); tw += g("dram__bytes_write.sum"); tt += t
-ind = max(n // 7, 1) if n > 7 else 1
+ind = max(n // 8, 1) if n > 8 else 1
 md += ["", f"Captured launches: {n} (= {ind} indicator(s)); {tt:.2f} ms serialised; DRAM traffic {tr + tw:.0f} MB (read {tr:.0f}, write {tw:.0f}).",
-       "SURVEY 8(d) algorithmic bytes of one C3 indicator are ~660 MB: the gathers of B' (20 MB after downsampling) and of the per-column terms hit "
-       "the 126 MB L2, so the kernel moves LESS than its algorithmic bytes from HBM -- at C3 it is bound by instruction issue (fp64 LLR + top-k select), "
-       "not by HBM (DESIGN.md 3.2)."]
+       "SURVEY 8(d) algorithmic bytes of one C3 indicator are ~664 MB: the gathers of B' (20 MB after downsampling) and of the per-column terms hit "
+       "the 126 MB L2, so the kernel moves LESS than its algorithmic bytes from HBM.  What binds it (DESIGN.md 3.2): CTA-owned bins wait at the "
+       "barrier that ends the count phase (`barrier` column), warp-owned bins are limited by shared memory per row (warps active) and spend ~30 % "
+       "of their instructions in the final sort; fp64 pipe utilisation is low after the level-1 integer cut (12.7 % of the cells reach the LLR)."]
 open(f"profiles/{tag}_k_rows_ncu_full.md", "w").write("\n".join(md) + "\n")
+import hashlib, os
+build = hashlib.sha1(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "universal_recommender_b200", "csrc",
+                                       "cco_kernels.cuh"), "rb").read()).hexdigest()[:12]
 json.dump({"source": f"profiles/{tag}_k_rows_ncu_full.md", "workload": "C3", "dram_bytes_per_indicator": (tr + tw) * 1e6 / ind,
-           "launches_per_indicator": n / ind}, open(f"profiles/{tag}_k_rows_traffic.json", "w"))
+           "launches_per_indicator": n / ind, "build": build}, open(f"profiles/{tag}_k_rows_traffic.json", "w"))
 print("\n".join(md[6:]))

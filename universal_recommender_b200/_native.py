@@ -57,6 +57,10 @@ class SynthTypeT(C.Structure):
                 ("item_cdf", C.POINTER(C.c_double)), ("item_perm", C.POINTER(C.c_int32))]
 
 
+class DictionaryT(C.Structure):
+    _fields_ = [("n", C.c_int64), ("offsets", C.POINTER(C.c_int64)), ("bytes", C.c_char_p)]
+
+
 class StatsT(C.Structure):
     _fields_ = [("n_users", C.c_int64), ("nnz_in_total", C.c_int64),
                 ("nnz_downsampled", C.c_int64 * 16), ("products", C.c_int64 * 16),
@@ -72,7 +76,7 @@ EXPORTS = [
     "cco_create", "cco_create_group", "cco_destroy", "cco_host_alloc", "cco_host_free", "cco_train", "cco_cooccurrences_idss",
     "cco_dataset_upload", "cco_train_dataset", "cco_dataset_free", "cco_timer_start", "cco_timer_stop",
     "cco_partition_rows", "cco_ingest", "cco_synth_ingest", "cco_dataset_shape", "cco_dataset_download",
-    "cco_dataset_copy_to_host",
+    "cco_dataset_copy_to_host", "cco_format_es_bulk", "cco_pop_model",
     "cco_result_num_matrices", "cco_result_row_range", "cco_result_matrix", "cco_result_stats", "cco_result_free",
     "cco_debug_cooccurrence", "cco_debug_downsample", "cco_debug_llr", "cco_free",
 ]
@@ -111,6 +115,10 @@ def lib():
     L.cco_ingest.argtypes = [C.c_void_p, C.c_int32, p(EventsT), C.c_int64, C.c_int32, p(C.c_int32), p(p(C.c_int32)), p(C.c_void_p)]
     L.cco_synth_ingest.argtypes = [C.c_void_p, C.c_int32, p(SynthTypeT), C.c_int64, p(C.c_double), p(C.c_int32), C.c_int32, C.c_int32, p(C.c_void_p)]
     L.cco_dataset_copy_to_host.argtypes = [C.c_void_p, C.c_int32, p(C.c_int64), p(C.c_int32)]
+    L.cco_format_es_bulk.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, p(C.c_char_p), p(DictionaryT), p(DictionaryT), p(C.c_void_p),
+                                     p(C.c_int64)]
+    L.cco_pop_model.argtypes = [C.c_void_p, C.c_int32, C.c_int64, p(C.c_int32), p(C.c_int64), C.c_int32, C.c_int64, C.c_int64, p(C.c_double),
+                                p(C.c_ubyte)]
     L.cco_dataset_shape.argtypes = [C.c_void_p, C.c_int32, p(C.c_int64), p(C.c_int32), p(C.c_int64)]
     L.cco_dataset_download.argtypes = [C.c_void_p, C.c_int32, p(p(C.c_int64)), p(p(C.c_int32))]
     L.cco_timer_start.argtypes = [C.c_void_p]

@@ -16,11 +16,13 @@
 #include <nvtx3/nvToolsExt.h>
 #include <condition_variable>
 #include <mutex>
+#include <string>
 #include <thread>
 #include <vector>
 
 #include "../../include/cco_b200.h"
 #include "cco_kernels.cuh"
+#include "cco_format.cuh"
 
 namespace cco {
 
@@ -159,6 +161,14 @@ struct cco_ctx {
   size_t arena_bytes = 0, arena_used = 0;
   int arena_live = 0;
   bool arena_registered = false;
+  // small per-train device scratch comes from slabs the context keeps (bump allocation: no CUDA call per buffer), and the
+  // per-train events come from a cached pool: a train of a small shape is bound by host API calls, not by its kernels
+  struct Slab { unsigned char *p; size_t cap; };
+  std::vector<Slab> slabs;
+  size_t slab_idx = 0, slab_off = 0;
+  bool slab_busy = false;
+  std::vector<cudaEvent_t> ev_timing, ev_plain;
+  size_t ev_timing_used = 0, ev_plain_used = 0;
   // group context: the leader owns one member context per GPU (members[0]->device = devices[0], ...)
   std::vector<cco_ctx *> members;
   GroupShared *gshared = nullptr;   // set on members
@@ -237,22 +247,56 @@ namespace cco {
 // per-call device arena on top of the stream-ordered allocator
 struct Arena {
   cudaStream_t s;
+  cco_ctx *c;   // non-null: buffers up to kSlabMax bytes are bump-allocated from the context's slabs
   std::vector<void *> ptrs;
-  explicit Arena(cudaStream_t st) : s(st) {}
+  static constexpr size_t kSlabMax = 8u << 20, kSlabBytes = 64u << 20;
+  explicit Arena(cudaStream_t st, cco_ctx *ctx = nullptr) : s(st), c(ctx && !ctx->slab_busy ? ctx : nullptr) {
+    if (c) {
+      c->slab_busy = true;
+      c->slab_idx = 0;
+      c->slab_off = 0;
+    }
+  }
   ~Arena() {
     for (void *p : ptrs) cudaFreeAsync(p, s);
+    if (c) c->slab_busy = false;
+  }
+  void *bump(size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    while (true) {
+      if (c->slab_idx < c->slabs.size()) {
+        cco_ctx::Slab &sl = c->slabs[c->slab_idx];
+        if (c->slab_off + bytes <= sl.cap) {
+          void *p = sl.p + c->slab_off;
+          c->slab_off += bytes;
+          return p;
+        }
+        ++c->slab_idx;
+        c->slab_off = 0;
+        continue;
+      }
+      void *p = nullptr;
+      if (cudaMalloc(&p, kSlabBytes) != cudaSuccess) return nullptr;   // warm-up trains only; kept until cco_destroy
+      c->slabs.push_back({(unsigned char *)p, kSlabBytes});
+    }
   }
   template <typename T>
   int alloc(T **out, size_t n) {
     void *p = nullptr;
     size_t bytes = std::max<size_t>(n * sizeof(T), 16);
+    if (c && bytes <= kSlabMax) {
+      p = bump(bytes);
+      if (!p) return set_error(CCO_E_OOM, "cudaMalloc(scratch slab) failed");
+      *out = (T *)p;
+      return CCO_OK;
+    }
     cudaError_t e = cudaMallocAsync(&p, bytes, s);
     if (e != cudaSuccess) return set_error(CCO_E_OOM, "cudaMallocAsync(%zu bytes): %s", bytes, cudaGetErrorString(e));
     ptrs.push_back(p);
     *out = (T *)p;
     return CCO_OK;
   }
-  void release(void *p) {
+  void release(void *p) {   // slab memory is simply not reused within a train
     for (size_t i = 0; i < ptrs.size(); ++i)
       if (ptrs[i] == p) {
         cudaFreeAsync(p, s);
@@ -261,6 +305,18 @@ struct Arena {
       }
   }
 };
+// cached events of a train (reset at its start)
+static int pooled_event(cco_ctx *c, bool timing, cudaEvent_t *out) {
+  std::vector<cudaEvent_t> &pool = timing ? c->ev_timing : c->ev_plain;
+  size_t &used = timing ? c->ev_timing_used : c->ev_plain_used;
+  if (used == pool.size()) {
+    cudaEvent_t e;
+    CK(timing ? cudaEventCreate(&e) : cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    pool.push_back(e);
+  }
+  *out = pool[used++];
+  return CCO_OK;
+}
 
 // NVTX ranges per stage (tracing); header-only NVTX3, a no-op unless a profiler is attached
 static inline void nvtx_push(const char *name) { nvtxRangePushA(name); }
@@ -487,12 +543,12 @@ static int nccl_check(int rc, const char *what) {
 }
 
 // Multi-GPU form of sampleDownAndBinarize.  Rank r holds (and samples) only its block of users.  Four collectives over
-// NVLink per train, no host round trip anywhere:
+// NVLink per train:
 //   (1) [caller] all-reduce of the raw column counts            -> the sampling rates
 //   (2) all-gather of the per-user kept counts (all matrices)   -> every rank scans the identical row_ptr
 //   (3) all-reduce of the post-sample column counts             -> marginals (nothing is re-counted on the gathered matrix)
-//   (4) all-gather of the sampled column blocks, each padded to the largest raw block (a size the host knows from the
-//       caller's row_ptr), then a pack kernel that reads the true block lengths from row_ptr on the device.
+//   (4) all-gather of the sampled column blocks, each padded to the largest sampled block (the block sizes come from the
+//       scanned row_ptr through one mailbox record: an event wait, not a stream sync), then a pack kernel.
 static int downsample_sharded_all(cco_ctx *c, Arena &ar, const std::vector<DevRaw> &raw, const std::vector<HeavyRows> &heavy,
                                   const std::vector<long long> &block_cap,
                                   long long U, const int32_t *raw_counts, int32_t *marg_all, const std::vector<long long> &col_off,
@@ -527,18 +583,26 @@ static int downsample_sharded_all(cco_ctx *c, Arena &ar, const std::vector<DevRa
   if (col_off[n_mats] > 0)
     CKR(nccl_check(g_nccl.AllReduce(marg_all, marg_all, (size_t)col_off[n_mats], kNcclInt32, kNcclSum, c->comm, s), "ncclAllReduce(marginals)"));
   std::vector<int32_t *> gathered(n_mats, nullptr);
+  // NCCL's all-gather moves equal counts per rank.  The raw block size (host-known) would do as the padding, but after
+  // downsampling a block is 2-3x smaller than its raw size at the 10M-user shapes (C4: 1.8 GB received per GPU, 4.7 ms).
+  // The sampled block sizes sit in row_ptr on the device: one mailbox record per train brings them to the host (one event
+  // wait, no stream-wide sync) and the gather is padded to the largest SAMPLED block only.
+  std::vector<uint32_t> edge((size_t)n_mats * (W + 1), 0);
   for (int i = 0; i < n_mats; ++i) {
     CKR(exclusive_sum_u32(c, ar, kept[i], dm[i].rp, U + 1));
     ar.release(kept[i]);
+    for (int q = 0; q <= W; ++q) CKR(mail_fetch(c, &edge[(size_t)i * (W + 1) + q], dm[i].rp + std::min<long long>((long long)q * S, U), 4));
   }
   CK(cudaEventRecord(stage_ev[1], s));
+  CKR(mail_wait(c));
+  std::vector<long long> cap(n_mats, 0);
   for (int i = 0; i < n_mats; ++i) {
-    const long long cap = block_cap[i];
-    CKR(ar.alloc(&dm[i].col, std::max<long long>(raw[i].nnz_cap, 1)));
-    if (cap == 0) continue;
-    CKR(ar.alloc(&gathered[i], (size_t)(cap * W)));
+    for (int q = 0; q < W; ++q) cap[i] = std::max<long long>(cap[i], (long long)edge[(size_t)i * (W + 1) + q + 1] - edge[(size_t)i * (W + 1) + q]);
+    CKR(ar.alloc(&dm[i].col, std::max<long long>(edge[(size_t)i * (W + 1) + W], 1)));
+    if (cap[i] == 0) continue;
+    CKR(ar.alloc(&gathered[i], (size_t)(cap[i] * W)));
     // this rank's block goes straight into its slot of the gather buffer, relative to the block's first entry
-    launch_write(c, raw[i], heavy[i], sc[i], dm[i].rp, dm[i].rp + row_base, gathered[i] + (size_t)r * cap);
+    launch_write(c, raw[i], heavy[i], sc[i], dm[i].rp, dm[i].rp + row_base, gathered[i] + (size_t)r * cap[i]);
     ar.release(sc[i].col_thr);
     ar.release(sc[i].keep);
   }
@@ -546,14 +610,14 @@ static int downsample_sharded_all(cco_ctx *c, Arena &ar, const std::vector<DevRa
   g_nccl.GroupStart();
   for (int i = 0; i < n_mats; ++i) {
     if (!gathered[i]) continue;
-    int rc = g_nccl.AllGather(gathered[i] + (size_t)r * block_cap[i], gathered[i], (size_t)block_cap[i], kNcclInt32, c->comm, s);
+    int rc = g_nccl.AllGather(gathered[i] + (size_t)r * cap[i], gathered[i], (size_t)cap[i], kNcclInt32, c->comm, s);
     if (rc != 0) { g_nccl.GroupEnd(); return nccl_check(rc, "ncclAllGather(column blocks)"); }
   }
   CKR(nccl_check(g_nccl.GroupEnd(), "ncclGroupEnd(column blocks)"));
   for (int i = 0; i < n_mats; ++i) {
     if (!gathered[i]) continue;
     dim3 grid((unsigned)std::max(1, std::min(c->sm_count * 8 / W, 1024)), (unsigned)W);
-    k_pack_blocks<<<grid, 256, 0, s>>>(W, S, U, block_cap[i], dm[i].rp, gathered[i], dm[i].col);
+    k_pack_blocks<<<grid, 256, 0, s>>>(W, S, U, cap[i], dm[i].rp, gathered[i], dm[i].col);
     c->launches++;
     ar.release(gathered[i]);
   }
@@ -1118,7 +1182,8 @@ static int train_dataset(cco_ctx *c, const cco_dataset *ds, const cco_indicator_
   cudaStream_t s = c->stream;
   const int n_mats = ds->n_mats;
   mail_reset(c);
-  Arena ar(s);
+  c->ev_timing_used = c->ev_plain_used = 0;
+  Arena ar(s, c);
   struct CopyJoin {  // destroyed before `ar`: no packed buffer is freed while the copy stream still reads it
     cco_ctx *c;
     ~CopyJoin() { cudaStreamSynchronize(c->copy_stream); }
@@ -1135,15 +1200,7 @@ static int train_dataset(cco_ctx *c, const cco_dataset *ds, const cco_indicator_
     }
   } guard{res};
   std::vector<IndicatorState> ist(n_mats);
-  struct EvGuard {
-    std::vector<IndicatorState> &v;
-    std::vector<cudaEvent_t> extra;
-    ~EvGuard() {
-      for (auto &x : v)
-        if (x.packed) cudaEventDestroy(x.packed);
-      for (auto e : extra) cudaEventDestroy(e);
-    }
-  } evg{ist, {}};
+  for (auto &x : ist) CKR(pooled_event(c, false, &x.packed));
   cco_stats_t &st = res->stats;
   st.n_mats = n_mats;
   st.n_users = ds->n_users;
@@ -1165,10 +1222,7 @@ static int train_dataset(cco_ctx *c, const cco_dataset *ds, const cco_indicator_
   CK(cudaEventRecord(c->ev[1], s));
   nvtx_push("cco:prepare");
   std::vector<cudaEvent_t> sev(8, nullptr);   // stage boundaries of the preparation (cco_stats_t.ms_prep_stage)
-  for (auto &e : sev) {
-    CK(cudaEventCreate(&e));
-    evg.extra.push_back(e);
-  }
+  for (auto &e : sev) CKR(pooled_event(c, true, &e));
   auto mark = [&](int k) { return cudaEventRecord(sev[k], s); };
   // raw column counts: this rank histograms its user block; ONE allreduce sums all matrices' counts
   long long total_cols = 0;
@@ -1269,10 +1323,7 @@ static int train_dataset(cco_ctx *c, const cco_dataset *ds, const cco_indicator_
   // indicators, software-pipelined: indicator i+1 is on the stream before the host waits for indicator i's record
   std::vector<IndicatorOut> io(n_mats);
   std::vector<cudaEvent_t> ev_rows(2 * n_mats, nullptr);
-  for (auto &e : ev_rows) {
-    CK(cudaEventCreate(&e));
-    evg.extra.push_back(e);
-  }
+  for (auto &e : ev_rows) CKR(pooled_event(c, true, &e));
   for (int i = 0; i < n_mats; ++i) {
     nvtx_push("cco:indicator");
     CKR(enqueue_indicator(c, ar, at_ptr, at_users, n_items_a, dm[0].marg, max_marg[0], max_marg[i], dm[i], n_users, i == 0, params[i],
@@ -1565,6 +1616,9 @@ int cco_destroy(cco_ctx_t *c) {
   if (c->arena_registered) cudaHostUnregister(c->arena);
   if (c->mail_h) cudaFreeHost(c->mail_h);
   for (auto &ev : c->mail_ev) cudaEventDestroy(ev);
+  for (auto &ev : c->ev_timing) cudaEventDestroy(ev);
+  for (auto &ev : c->ev_plain) cudaEventDestroy(ev);
+  for (auto &sl : c->slabs) cudaFree(sl.p);
   for (auto &ev : c->ev)
     if (ev) cudaEventDestroy(ev);
   for (auto &ev : c->tev)
@@ -2020,6 +2074,210 @@ int cco_result_free(cco_result_t *r) {
       if (p) r->ctx->pinned_put(p);
   }
   delete r;
+  return CCO_OK;
+}
+
+// ---- indicator model -> Elasticsearch bulk body (cco_format.cuh) --------------------------------------
+namespace cco {
+static int upload_dict(cco_ctx *c, Arena &ar, const cco_dictionary_t &d, DevDict *raw) {
+  if (d.n < 0 || (d.n > 0 && (!d.offsets || (d.offsets[d.n] > 0 && !d.bytes)))) return set_error(CCO_E_INVALID_ARG, "bad dictionary");
+  long long *off;
+  unsigned char *bytes;
+  const long long nb = d.n > 0 ? d.offsets[d.n] : 0;
+  CKR(ar.alloc(&off, d.n + 1));
+  CKR(ar.alloc(&bytes, std::max<long long>(nb, 1)));
+  if (d.n > 0) {
+    CK(cudaMemcpyAsync(off, d.offsets, sizeof(int64_t) * ((size_t)d.n + 1), cudaMemcpyHostToDevice, c->stream));
+    if (nb > 0) CK(cudaMemcpyAsync(bytes, d.bytes, (size_t)nb, cudaMemcpyHostToDevice, c->stream));
+  } else {
+    CK(cudaMemsetAsync(off, 0, 8, c->stream));
+  }
+  raw->off = off;
+  raw->bytes = bytes;
+  raw->n = d.n;
+  return CCO_OK;
+}
+// JSON-escape every string of a device dictionary (two passes: lengths, scan, bytes)
+static int escape_dict(cco_ctx *c, Arena &ar, const DevDict &raw, DevDict *esc) {
+  long long *len, *off;
+  CKR(ar.alloc(&len, raw.n + 1));
+  CKR(ar.alloc(&off, raw.n + 1));
+  CK(cudaMemsetAsync(len + raw.n, 0, 8, c->stream));
+  if (raw.n > 0) {
+    k_escape_len<<<grid_for(raw.n, 256, c->sm_count), 256, 0, c->stream>>>(raw.n, raw.off, raw.bytes, len);
+    c->launches++;
+  }
+  CKR(exclusive_sum_i64(c, ar, len, off, raw.n + 1));
+  long long total = 0;
+  CK(cudaMemcpyAsync(&total, off + raw.n, 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  unsigned char *bytes;
+  CKR(ar.alloc(&bytes, std::max<long long>(total, 1)));
+  if (raw.n > 0) {
+    k_escape_write<<<grid_for(raw.n, 256, c->sm_count), 256, 0, c->stream>>>(raw.n, raw.off, raw.bytes, off, bytes);
+    c->launches++;
+  }
+  esc->off = off;
+  esc->bytes = bytes;
+  esc->n = raw.n;
+  ar.release(len);
+  return CCO_OK;
+}
+}  // namespace cco
+
+int cco_format_es_bulk(cco_ctx_t *ctx, const cco_result_t *res, int32_t n_names, const char *const *names,
+                       const cco_dictionary_t *row_ids, const cco_dictionary_t *col_ids, char **out_bytes, int64_t *out_len) {
+  if (!ctx || !res || !names || !row_ids || !col_ids || !out_bytes || !out_len) return set_error(CCO_E_INVALID_ARG, "null argument");
+  const int n_ind = (int)res->mats.size();
+  if (n_names != n_ind) return set_error(CCO_E_INVALID_ARG, "%d event names for %d indicators", n_names, n_ind);
+  if (n_ind < 1 || n_ind > kMaxFormatIndicators) return set_error(CCO_E_UNSUPPORTED, "1..%d indicators", kMaxFormatIndicators);
+  cco_ctx *c = ctx->members.empty() ? ctx : ctx->members[0];   // a group's merged model is formatted on its first GPU
+  const int64_t row_lo = res->mats[0].row_begin, row_hi = res->mats[0].row_end;
+  for (int i = 0; i < n_ind; ++i) {
+    const ResultMat &m = res->mats[i];
+    if (m.row_begin != row_lo || m.row_end != row_hi) return set_error(CCO_E_INVALID_ARG, "indicators cover different row ranges");
+    if (!m.row_ptr || (m.row_ptr[row_hi - row_lo] > 0 && !m.col)) return set_error(CCO_E_INVALID_ARG, "indicator %d has no column array on the host", i);
+    if (col_ids[i].n < m.n_cols) return set_error(CCO_E_INVALID_ARG, "column dictionary %d has %lld ids for %d columns", i, (long long)col_ids[i].n, m.n_cols);
+    if (!names[i]) return set_error(CCO_E_INVALID_ARG, "null event name");
+  }
+  if (row_ids->n < row_hi) return set_error(CCO_E_INVALID_ARG, "row dictionary has %lld ids, rows go up to %lld", (long long)row_ids->n, (long long)row_hi);
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  Arena ar(s);
+  nvtx_push("cco:format_es_bulk");
+  struct Pop { ~Pop() { nvtx_pop(); } } pop;
+  FormatArgs fa;
+  memset(&fa, 0, sizeof fa);
+  fa.n_rows = (int32_t)(row_hi - row_lo);
+  fa.row_id_base = row_lo;
+  fa.n_ind = n_ind;
+  DevDict raw;
+  CKR(upload_dict(c, ar, *row_ids, &raw));
+  CKR(escape_dict(c, ar, raw, &fa.row_ids));
+  // event names as one more tiny dictionary
+  {
+    std::vector<int64_t> noff(n_ind + 1, 0);
+    std::string blob;
+    for (int i = 0; i < n_ind; ++i) {
+      blob += names[i];
+      noff[i + 1] = (int64_t)blob.size();
+    }
+    cco_dictionary_t nd = {n_ind, noff.data(), blob.data()};
+    DevDict nraw, nesc;
+    CKR(upload_dict(c, ar, nd, &nraw));
+    CK(cudaStreamSynchronize(s));   // noff / blob are locals
+    CKR(escape_dict(c, ar, nraw, &nesc));
+    std::vector<long long> eoff(n_ind + 1);
+    CK(cudaMemcpyAsync(eoff.data(), nesc.off, sizeof(long long) * ((size_t)n_ind + 1), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    fa.names = nesc.bytes;
+    for (int i = 0; i <= n_ind; ++i) fa.name_off[i] = (int32_t)eoff[i];
+  }
+  for (int i = 0; i < n_ind; ++i) {
+    const ResultMat &m = res->mats[i];
+    CKR(upload_dict(c, ar, col_ids[i], &raw));
+    CKR(escape_dict(c, ar, raw, &fa.col_ids[i]));
+    const long long n_my = row_hi - row_lo, nnz = m.row_ptr[n_my] - m.row_ptr[0];
+    long long *d_rp;
+    int32_t *d_col;
+    CKR(ar.alloc(&d_rp, n_my + 1));
+    CKR(ar.alloc(&d_col, std::max<long long>(nnz, 1)));
+    CK(cudaMemcpyAsync(d_rp, m.row_ptr, sizeof(int64_t) * ((size_t)n_my + 1), cudaMemcpyHostToDevice, s));
+    if (nnz > 0) CK(cudaMemcpyAsync(d_col, m.col + m.row_ptr[0], sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, s));
+    if (m.row_ptr[0] != 0) {   // a group member's slice is rebased inside the merged arrays: bring it back to 0
+      k_add_i64<<<grid_for(n_my + 1, 256, c->sm_count, 2), 256, 0, s>>>(n_my + 1, -(long long)m.row_ptr[0], d_rp);
+      c->launches++;
+    }
+    fa.row_ptr[i] = d_rp;
+    fa.col[i] = d_col;
+  }
+  long long *doc_len, *doc_off;
+  CKR(ar.alloc(&doc_len, fa.n_rows + 1));
+  CKR(ar.alloc(&doc_off, fa.n_rows + 1));
+  CK(cudaMemsetAsync(doc_len + fa.n_rows, 0, 8, s));
+  if (fa.n_rows > 0) {
+    k_doc_len<<<grid_for(fa.n_rows, 256, c->sm_count), 256, 0, s>>>(fa, doc_len);
+    c->launches++;
+  }
+  CKR(exclusive_sum_i64(c, ar, doc_len, doc_off, (long long)fa.n_rows + 1));
+  long long total = 0;
+  CK(cudaMemcpyAsync(&total, doc_off + fa.n_rows, 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  unsigned char *d_out;
+  CKR(ar.alloc(&d_out, std::max<long long>(total, 1)));
+  if (fa.n_rows > 0 && total > 0) {
+    k_doc_write<<<grid_for((long long)fa.n_rows * 32, 256, c->sm_count), 256, 0, s>>>(fa, doc_off, d_out);
+    c->launches++;
+  }
+  char *host = (char *)ctx->pinned_get((size_t)std::max<long long>(total, 1), /*for_result=*/false);
+  if (!host) return set_error(CCO_E_OOM, "pinned host allocation failed");
+  if (total > 0) CK(cudaMemcpyAsync(host, d_out, (size_t)total, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  CK(cudaGetLastError());
+  *out_bytes = host;
+  *out_len = total;
+  return CCO_OK;
+}
+
+// ---- PopModel rank histograms -------------------------------------------------------------------------
+int cco_pop_model(cco_ctx_t *ctx, int32_t mode, int64_t n_events, const int32_t *item, const int64_t *time_ms, int32_t n_items,
+                  int64_t start_ms, int64_t end_ms, double *score, unsigned char *present) {
+  if (!ctx || n_events < 0 || n_items < 0 || (n_events > 0 && (!item || !time_ms)) || (n_items > 0 && (!score || !present)))
+    return set_error(CCO_E_INVALID_ARG, "bad argument");
+  if (mode < CCO_POP_POPULAR || mode > CCO_POP_HOT) return set_error(CCO_E_INVALID_ARG, "mode must be CCO_POP_POPULAR, _TRENDING or _HOT");
+  if (end_ms < start_ms) return set_error(CCO_E_INVALID_ARG, "end before start (Joda Interval would throw)");
+  if (n_items == 0) return CCO_OK;
+  cco_ctx *c = ctx->members.empty() ? ctx : ctx->members[0];
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  Arena ar(s);
+  nvtx_push("cco:pop_model");
+  struct Pop { ~Pop() { nvtx_pop(); } } pop;
+  PopArgs a;
+  memset(&a, 0, sizeof a);
+  a.n_items = n_items;
+  const long long dur = end_ms - start_ms;
+  if (mode == CCO_POP_POPULAR) {
+    a.n_buckets = 1;
+    a.edge[0] = start_ms;
+    a.edge[1] = end_ms;
+  } else if (mode == CCO_POP_TRENDING) {   // PopModel.scala:134-138: halfInterval = durationMillis / 2
+    a.n_buckets = 2;
+    a.edge[0] = start_ms;
+    a.edge[1] = start_ms + dur / 2;
+    a.edge[2] = end_ms;
+  } else {                                  // PopModel.scala:159-164: older = dur / 3, middle = the same length, newer = the rest
+    a.n_buckets = 3;
+    a.edge[0] = start_ms;
+    a.edge[1] = start_ms + dur / 3;
+    a.edge[2] = a.edge[1] + dur / 3;
+    a.edge[3] = end_ms;
+  }
+  int32_t *d_item, *d_counts;
+  long long *d_t;
+  unsigned long long *d_tot;
+  double *d_score;
+  unsigned char *d_present;
+  CKR(ar.alloc(&d_item, std::max<long long>(n_events, 1)));
+  CKR(ar.alloc(&d_t, std::max<long long>(n_events, 1)));
+  CKR(ar.alloc(&d_counts, (size_t)a.n_buckets * n_items));
+  CKR(ar.alloc(&d_tot, 4));
+  CKR(ar.alloc(&d_score, n_items));
+  CKR(ar.alloc(&d_present, n_items));
+  CK(cudaMemsetAsync(d_counts, 0, sizeof(int32_t) * (size_t)a.n_buckets * n_items, s));
+  CK(cudaMemsetAsync(d_tot, 0, 32, s));
+  if (n_events > 0) {
+    CK(cudaMemcpyAsync(d_item, item, sizeof(int32_t) * (size_t)n_events, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_t, time_ms, sizeof(int64_t) * (size_t)n_events, cudaMemcpyHostToDevice, s));
+    k_pop_count<<<grid_for(n_events, 256, c->sm_count), 256, 0, s>>>(n_events, d_item, d_t, a, d_counts, d_tot);
+    c->launches++;
+  }
+  k_pop_score<<<grid_for(n_items, 256, c->sm_count), 256, 0, s>>>(a, mode, d_counts, d_tot, d_score, d_present);
+  c->launches++;
+  CK(cudaMemcpyAsync(score, d_score, sizeof(double) * (size_t)n_items, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(present, d_present, (size_t)n_items, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  CK(cudaGetLastError());
   return CCO_OK;
 }
 

@@ -175,6 +175,51 @@ class CcoContext:
     def free_result(self, handle):
         self._L.cco_result_free(handle)
 
+    # ---- next row: PopModel rank histograms ---------------------------------------------------------------
+    def pop_model(self, mode: str, items, times_ms, n_items: int, start_ms: int, end_ms: int):
+        """PopModel.calcPopular / calcTrending / calcHot (PopModel.scala:113-182) -> {item index: score} for the items the
+        reference's RDD would contain."""
+        code = {"popular": 0, "trending": 1, "hot": 2}[mode]
+        it = np.ascontiguousarray(items, dtype=np.int32)
+        tm = np.ascontiguousarray(times_ms, dtype=np.int64)
+        score = np.zeros(max(n_items, 1), dtype=np.float64)
+        present = np.zeros(max(n_items, 1), dtype=np.uint8)
+        N.check(self._L.cco_pop_model(self._h, code, len(it), it.ctypes.data_as(C.POINTER(C.c_int32)), tm.ctypes.data_as(C.POINTER(C.c_int64)),
+                                      n_items, int(start_ms), int(end_ms), score.ctypes.data_as(C.POINTER(C.c_double)),
+                                      present.ctypes.data_as(C.POINTER(C.c_ubyte))))
+        return {int(j): float(score[j]) for j in np.nonzero(present[:n_items])[0]}
+
+    # ---- next row (SURVEY.md 8f-2): the model as the Elasticsearch bulk body -------------------------------------------
+    @staticmethod
+    def _dictionary(ids):
+        """list of id strings -> (DictionaryT, keep-alive): UTF-8 bytes + offsets"""
+        enc = [x.encode("utf-8") for x in ids]
+        off = np.zeros(len(enc) + 1, dtype=np.int64)
+        np.cumsum([len(b) for b in enc], out=off[1:])
+        blob = b"".join(enc)
+        buf = C.create_string_buffer(blob, max(len(blob), 1))
+        return N.DictionaryT(len(enc), off.ctypes.data_as(C.POINTER(C.c_int64)), C.cast(buf, C.c_char_p)), (off, buf)
+
+    def format_es_bulk(self, handle, names, row_ids, col_ids) -> bytes:
+        """cco_format_es_bulk on a kept result (train_csr(..., keep=True)): one Elasticsearch bulk index action per row,
+        `{"index":{"_id":id}}\\n{"id":id,"<event>":[ordered correlator ids],...}\\n` -- what toStringMapRDD + URModel.save +
+        saveToEs produce for the reference (package.scala:82-110, URModel.scala:47-102, EsClient.scala:300-313)."""
+        n = len(names)
+        keep = []
+        rd, k = self._dictionary(row_ids)
+        keep.append(k)
+        cds = (N.DictionaryT * n)()
+        for i, ids in enumerate(col_ids):
+            cds[i], k = self._dictionary(ids)
+            keep.append(k)
+        nm = (C.c_char_p * n)(*[x.encode("utf-8") for x in names])
+        out, ln = C.c_void_p(), C.c_int64()
+        N.check(self._L.cco_format_es_bulk(self._h, handle, n, nm, C.byref(rd), cds, C.byref(out), C.byref(ln)))
+        try:
+            return C.string_at(out.value, ln.value)
+        finally:
+            self._L.cco_host_free(self._h, out)
+
     def train_csr(self, mats: Sequence[tuple[int, int, np.ndarray, np.ndarray]], params: Sequence[tuple[int, int, Optional[float]]],
                   seed: int, flags: int = 0, copy_arrays: bool = True, keep: bool = False):
         """Raw entry (cco_train): mats = [(n_rows, n_cols, row_ptr int64, col_idx int32)], params = [(m, k, minLLR|None)].

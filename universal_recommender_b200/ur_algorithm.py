@@ -35,6 +35,10 @@ class URAlgorithmParams:
     indicators: Optional[Sequence[IndicatorParams]] = None
     seed: Optional[int] = None
     recsModel: str = "all"
+    # not an engine.json key of the reference: selects the literal Int/Int row sample rate recalled from Mahout 0.13.0's
+    # sampleDownAndBinarize (every interaction of a user above maxItemsPerUser is dropped) instead of the
+    # real division min(m, d) / d this build defaults to (INTEGRATION.md "Deviation to know about")
+    rowRateIntDiv: bool = False
 
     @staticmethod
     def from_engine_json(algo_params: dict) -> "URAlgorithmParams":
@@ -45,7 +49,8 @@ class URAlgorithmParams:
             maxCorrelatorsPerEventType=algo_params.get("maxCorrelatorsPerEventType"),
             indicators=None if ind is None else [IndicatorParams(i["name"], i.get("maxItemsPerUser"),
                                                                  i.get("maxCorrelatorsPerItem"), i.get("minLLR")) for i in ind],
-            seed=algo_params.get("seed"), recsModel=algo_params.get("recsModel", "all"))
+            seed=algo_params.get("seed"), recsModel=algo_params.get("recsModel", "all"),
+            rowRateIntDiv=bool(algo_params.get("rowRateIntDiv", False)))
 
 
 def calc_all(actions: Sequence[tuple[str, IndexedDataset]], ap: URAlgorithmParams,
@@ -59,6 +64,8 @@ def calc_all(actions: Sequence[tuple[str, IndexedDataset]], ap: URAlgorithmParam
     if ap.recsModel == "backfill":
         return []  # calcPop only: no CCO (URAlgorithm.scala:296)
     seed = ap.seed if ap.seed is not None else int(time.time() * 1000)   # System.currentTimeMillis() (:325,345)
+    if ap.rowRateIntDiv:
+        flags |= 1   # CCO_FLAG_ROWRATE_INTDIV
     ids = [d for _, d in actions]
     if not ap.indicators:
         out = SimilarityAnalysis.cooccurrencesIDSs(
