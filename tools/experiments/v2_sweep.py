@@ -1,4 +1,6 @@
-"""Development: sweep k_rows2's development switches (CCO_V2_TUNE) -- parity on a few workloads + C3 row-kernel time."""
+"""EXPERIMENT RECORD (profiles/r02_k_rows2_experiment.md): the CCO_ROWS_IMPL / CCO_V2_TUNE switches this script sets existed
+only while tools/experiments/cco_rows2.cuh was compiled into the library; kept to show how the A/B numbers were taken.
+Development: sweep k_rows2's development switches (CCO_V2_TUNE) -- parity on a few workloads + C3 row-kernel time."""
 import os, subprocess, sys
 here = os.path.dirname(os.path.abspath(__file__))
 CHILD = r'''

@@ -654,7 +654,7 @@ static int launch_rows_t(cco_ctx *c, const RowArgs &a, BinCfg &cfg, cudaStream_t
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem));
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, CTA, cfg.smem));
   // 4 waves of CTAs over the work-sorted row list: a CTA that draws cheap rows retires early and the hardware
-  // scheduler backfills, which balances the tail better than one persistent wave (tools/tune_rows.py: -6 % at C3)
+  // scheduler backfills, which balances the tail better than one persistent wave (round-1 launch sweep: -6 % at C3)
   kern<<<c->sm_count * std::max(occ, 1) * 4, CTA, cfg.smem, st>>>(a);
   cfg.ctas_per_sm = occ;
   c->launches++;
@@ -686,7 +686,7 @@ static BinCfg make_cfg(cco_ctx *c, int group, int want_slots, int top_k, int n_c
   size_t avail = (c->smem_optin - 1024) / groups;  // slack for static shared memory
   int max_slots = (int)((avail - fixed) / 4) & ~1023;
   f.slots = std::min(want_slots, max_slots);
-  f.cap = f.slots / 2;  // load factor <= 1/2: 2/3 and 3/4 are 8 % and 17 % slower (probe chains), tools/tune_rows.py
+  f.cap = f.slots / 2;  // load factor <= 1/2: 2/3 and 3/4 are 8 % and 17 % slower (probe chains), round-1 launch sweep
   f.dense = n_cols_b <= f.slots;
   f.region = (fixed + (size_t)f.slots * 4 + 15) & ~(size_t)15;
   f.smem = f.region * groups;
@@ -762,7 +762,7 @@ static int enqueue_indicator(cco_ctx *c, Arena &ar, const uint32_t *at_ptr, cons
   std::vector<BinSpec> spec = {{1024, 1 << 20, 0xffffffffu}, {1024, 1 << 20, 0xffffffffu}, {512, 16384, 8192u}, {256, 8192, 4096u}};
   if (warp_ok) {
     // rows of 1025..2048 products: a 128-thread CTA shares one 4096-word table -- a warp-owned 4096-word table leaves
-    // too few warps per SM (tools/tune_rows.py: -4 % at C3); up to 1024 products rows are warp-owned
+    // too few warps per SM (round-1 launch sweep: -4 % at C3); up to 1024 products rows are warp-owned
     spec.push_back({128, 4096, 2048u});
     spec.push_back({32, 2048, 1024u});
     spec.push_back({32, 1024, 512u});
