@@ -141,6 +141,7 @@ struct cco_ctx {
   cudaEvent_t tev[2] = {};
   cudaEvent_t copy_ev[2] = {};
   cudaStream_t bin_stream[8] = {};
+  cudaStream_t sched_stream = nullptr;   // row scheduling of indicator i+1 runs here, beside the row kernels of indicator i
   cudaEvent_t bin_ev[9] = {};
   std::vector<PinnedBuf> pinned;
   std::mutex mu;
@@ -399,12 +400,13 @@ static int exclusive_sum_u32(cco_ctx *c, Arena &ar, const uint32_t *in, uint32_t
   ar.release(tmp);
   return CCO_OK;
 }
-static int exclusive_sum_i64(cco_ctx *c, Arena &ar, const long long *in, long long *out, long long n) {
+static int exclusive_sum_i64(cco_ctx *c, Arena &ar, const long long *in, long long *out, long long n, cudaStream_t on = nullptr) {
+  if (!on) on = c->stream;
   size_t tb = 0;
-  CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, in, out, n, c->stream));
+  CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, in, out, n, on));
   void *tmp;
-  CKR(ar.alloc((char **)&tmp, tb));
-  CK(cub::DeviceScan::ExclusiveSum(tmp, tb, in, out, n, c->stream));
+  CKR(ar.alloc((char **)&tmp, tb));   // a few KB: always slab memory when the arena has slabs
+  CK(cub::DeviceScan::ExclusiveSum(tmp, tb, in, out, n, on));
   ar.release(tmp);
   return CCO_OK;
 }
@@ -711,8 +713,8 @@ struct IndicatorState {
 
 static int enqueue_indicator(cco_ctx *c, Arena &ar, const uint32_t *at_ptr, const int32_t *at_users, int32_t n_items_a,
                              const int32_t *marg_a, int32_t max_marg_a, int32_t max_marg_b, const DevMat &B, long long n_users,
-                             bool self, const cco_indicator_params_t &prm, uint32_t flags, bool emit_all, cudaEvent_t ev_begin,
-                             cudaEvent_t ev_end, IndicatorState *st) {
+                             bool self, const cco_indicator_params_t &prm, uint32_t flags, bool emit_all, cudaEvent_t inputs_ready,
+                             cudaEvent_t ev_begin, cudaEvent_t ev_end, IndicatorState *st) {
   cudaStream_t s = c->stream;
   const int32_t n_cols_b = B.n_cols;
   const int rank = c->rank, world = c->world;
@@ -720,10 +722,20 @@ static int enqueue_indicator(cco_ctx *c, Arena &ar, const uint32_t *at_ptr, cons
   st->n_cols_b = n_cols_b;
   st->emit_all = emit_all;
   // 1. work per output row, rank partition, schedule --------------------------------------------------
+  // The schedule reads only the prepared matrices, so it does not have to queue behind the previous indicator's row
+  // kernels: with `inputs_ready` (recorded on s once the preparation is complete) it runs on the scheduling stream and s
+  // joins it before the bins launch.  Everything it touches must then be slab memory (no stream-ordered allocation on s).
   uint32_t *row_work, *masked, *sorted_work;
   unsigned long long *work64;
   long long *work_prefix;
   int32_t *ids, *rows_sorted, *d_pb = nullptr;
+  size_t sort_tb = 0;
+  if (n_items_a > 0)
+    CK(cub::DeviceRadixSort::SortPairsDescending(nullptr, sort_tb, (const uint32_t *)nullptr, (uint32_t *)nullptr, (const int32_t *)nullptr,
+                                                 (int32_t *)nullptr, n_items_a, 0, 32, s));
+  const bool beside = inputs_ready && ar.c && ((size_t)n_items_a + 1) * 8 <= Arena::kSlabMax && sort_tb <= Arena::kSlabMax;
+  cudaStream_t ss = beside ? c->sched_stream : s;
+  if (beside) CK(cudaStreamWaitEvent(ss, inputs_ready, 0));
   CKR(ar.alloc(&row_work, n_items_a + 1));
   CKR(ar.alloc(&masked, n_items_a + 1));
   CKR(ar.alloc(&work64, n_items_a + 1));
@@ -731,25 +743,23 @@ static int enqueue_indicator(cco_ctx *c, Arena &ar, const uint32_t *at_ptr, cons
   CKR(ar.alloc(&ids, n_items_a + 1));
   CKR(ar.alloc(&sorted_work, n_items_a + 1));
   CKR(ar.alloc(&rows_sorted, n_items_a + 1));
-  CK(cudaMemsetAsync(work64 + n_items_a, 0, 8, s));
-  k_row_work<<<grid_for((long long)n_items_a * kSG, 256, c->sm_count), 256, 0, s>>>(n_items_a, at_ptr, at_users, B.rp,
-                                                                                 row_work, work64, ids, nullptr);
+  CK(cudaMemsetAsync(work64 + n_items_a, 0, 8, ss));
+  k_row_work<<<grid_for((long long)n_items_a * kSG, 256, c->sm_count), 256, 0, ss>>>(n_items_a, at_ptr, at_users, B.rp,
+                                                                                  row_work, work64, ids, nullptr);
   c->launches++;
-  CKR(exclusive_sum_i64(c, ar, (const long long *)work64, work_prefix, (long long)n_items_a + 1));
+  CKR(exclusive_sum_i64(c, ar, (const long long *)work64, work_prefix, (long long)n_items_a + 1, ss));
   if (world > 1) {
     // contiguous item ranges balanced by work prefix, identical on every rank; they never leave the device
     CKR(ar.alloc(&d_pb, world + 1));
-    k_partition_rows<<<1, ((world + 1 + 31) / 32) * 32, 0, s>>>(work_prefix, n_items_a, world, d_pb);
+    k_partition_rows<<<1, ((world + 1 + 31) / 32) * 32, 0, ss>>>(work_prefix, n_items_a, world, d_pb);
     c->launches++;
   }
-  k_mask_work<<<grid_for(n_items_a, 256, c->sm_count), 256, 0, s>>>(n_items_a, row_work, d_pb, rank, masked);
+  k_mask_work<<<grid_for(n_items_a, 256, c->sm_count), 256, 0, ss>>>(n_items_a, row_work, d_pb, rank, masked);
   c->launches++;
   if (n_items_a > 0) {
-    size_t tb = 0;
-    CK(cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, masked, sorted_work, ids, rows_sorted, n_items_a, 0, 32, s));
     void *tmp;
-    CKR(ar.alloc((char **)&tmp, tb));
-    CK(cub::DeviceRadixSort::SortPairsDescending(tmp, tb, masked, sorted_work, ids, rows_sorted, n_items_a, 0, 32, s));
+    CKR(ar.alloc((char **)&tmp, sort_tb));
+    CK(cub::DeviceRadixSort::SortPairsDescending(tmp, sort_tb, masked, sorted_work, ids, rows_sorted, n_items_a, 0, 32, ss));
     ar.release(tmp);
   }
   // 2. bins -----------------------------------------------------------------------------------------
@@ -800,8 +810,14 @@ static int enqueue_indicator(cco_ctx *c, Arena &ar, const uint32_t *at_ptr, cons
   BinThresholds bt;
   memset(&bt, 0, sizeof bt);
   for (int b = 0; b < kBins; ++b) bt.t[b] = h_thr[b];
-  k_bin_bounds<<<1, 32, 0, s>>>(n_items_a, sorted_work, kBins, bt, d_bounds);
+  k_bin_bounds<<<1, 32, 0, ss>>>(n_items_a, sorted_work, kBins, bt, d_bounds);
   c->launches++;
+  if (beside) {
+    cudaEvent_t scheduled;
+    CKR(pooled_event(c, false, &scheduled));
+    CK(cudaEventRecord(scheduled, ss));
+    CK(cudaStreamWaitEvent(s, scheduled, 0));
+  }
   // per-column constants of B' for the fused LLR
   ColTerm *col_terms;
   CKR(ar.alloc(&col_terms, std::max<int32_t>(n_cols_b, 1)));
@@ -1186,7 +1202,10 @@ static int train_dataset(cco_ctx *c, const cco_dataset *ds, const cco_indicator_
   Arena ar(s, c);
   struct CopyJoin {  // destroyed before `ar`: no packed buffer is freed while the copy stream still reads it
     cco_ctx *c;
-    ~CopyJoin() { cudaStreamSynchronize(c->copy_stream); }
+    ~CopyJoin() {
+      cudaStreamSynchronize(c->copy_stream);
+      cudaStreamSynchronize(c->sched_stream);   // error paths: no schedule kernel outlives the train's slab memory
+    }
   } copy_join{c};
   cco_result *res = new cco_result();
   res->ctx = c;
@@ -1327,7 +1346,7 @@ static int train_dataset(cco_ctx *c, const cco_dataset *ds, const cco_indicator_
   for (int i = 0; i < n_mats; ++i) {
     nvtx_push("cco:indicator");
     CKR(enqueue_indicator(c, ar, at_ptr, at_users, n_items_a, dm[0].marg, max_marg[0], max_marg[i], dm[i], n_users, i == 0, params[i],
-                          flags, false, ev_rows[2 * i], ev_rows[2 * i + 1], &ist[i]));
+                          flags, false, c->ev[2], ev_rows[2 * i], ev_rows[2 * i + 1], &ist[i]));
     nvtx_pop();
     if (i > 0) CKR(finish_indicator(c, &ist[i - 1], flags, i - 1, &res->mats[i - 1], &io[i - 1]));
   }
@@ -1478,6 +1497,7 @@ static int ctx_init_device(cco_ctx *c) {
   for (auto &ev : c->tev) CK(cudaEventCreate(&ev));
   for (auto &ev : c->copy_ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   for (auto &st : c->bin_stream) CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->sched_stream, cudaStreamNonBlocking));
   for (auto &ev : c->bin_ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   CK(cudaHostAlloc((void **)&c->mail_h, kMailBytes, cudaHostAllocMapped | cudaHostAllocPortable));
   CK(cudaHostGetDevicePointer((void **)&c->mail_d, c->mail_h, 0));
@@ -1627,6 +1647,7 @@ int cco_destroy(cco_ctx_t *c) {
     if (ev) cudaEventDestroy(ev);
   for (auto &st : c->bin_stream)
     if (st) cudaStreamDestroy(st);
+  if (c->sched_stream) cudaStreamDestroy(c->sched_stream);
   for (auto &ev : c->bin_ev)
     if (ev) cudaEventDestroy(ev);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -2416,7 +2437,7 @@ int cco_debug_cooccurrence(cco_ctx_t *c, const cco_csr_t *a, const cco_csr_t *b,
       if (p) c->pinned_put(p);
   };
   int rc = enqueue_indicator(c, ar, at_ptr, at_users, n_items_a, dm[0].marg, max_marg_ab[0], max_marg_ab[1], dm[1], a->n_rows, false, p1,
-                             0, true, nullptr, nullptr, &ist);
+                             0, true, nullptr, nullptr, nullptr, &ist);
   if (rc == CCO_OK) rc = finish_indicator(c, &ist, 0, 0, &rm, &io);
   cudaStreamSynchronize(c->copy_stream);
   if (rc != CCO_OK) {
