@@ -22,6 +22,7 @@
 
 #include "../../include/cco_b200.h"
 #include "cco_kernels.cuh"
+#include "cco_sampler.cuh"
 #include "cco_format.cuh"
 
 namespace cco {
@@ -493,30 +494,35 @@ static int sample_scratch(cco_ctx *c, Arena &ar, const DevRaw &raw, const int32_
   }
   return CCO_OK;
 }
-static void launch_count(cco_ctx *c, const DevRaw &raw, const HeavyRows &h, const SampleScratch &sc, int32_t m, int32_t seed,
-                         uint32_t flags, uint32_t *kept, int32_t *new_counts) {
-  if (raw.n_rows <= 0) return;
+// pass 1 (k_sample_count, cco_sampler.cuh): entry-parallel; `kept` must be zero for the block's rows; `bad` (nullable) is the
+// device verdict of k_check_rows -- a malformed matrix keeps nothing, so pass 2 can never write more than row_ptr promises
+static void launch_count(cco_ctx *c, const DevRaw &raw, const SampleScratch &sc, int32_t m, int32_t seed, uint32_t flags, const int *bad,
+                         uint32_t *kept, int32_t *new_counts) {
+  if (raw.n_rows <= 0 || raw.nnz <= 0) return;
   const long long q_lo = raw.q_base, q_hi = raw.q_base + raw.nnz;
-  k_downsample_count<kSG><<<grid_for(raw.n_rows * kSG, 256, c->sm_count), 256, 0, c->stream>>>(raw.n_rows, raw.row_base, raw.rp, raw.col, raw.n_cols,
-                                                                                             q_lo, q_hi, sc.col_thr, m, seed, flags, nullptr, nullptr,
-                                                                                             kept, new_counts, sc.keep);
-  k_downsample_count<32><<<c->sm_count * 4, 256, 0, c->stream>>>(raw.n_rows, raw.row_base, raw.rp, raw.col, raw.n_cols, q_lo, q_hi, sc.col_thr, m,
-                                                                 seed, flags, h.list, h.n, kept, new_counts, sc.keep);
-  c->launches += 2;
+  const long long n_chunks = (raw.nnz + kSampleChunk - 1) / kSampleChunk;
+  k_sample_count<<<grid_for(n_chunks * 32, 256, c->sm_count), 256, 0, c->stream>>>(raw.n_rows, raw.row_base, raw.rp, raw.col, raw.n_cols, q_lo, q_hi,
+                                                                                  sc.col_thr, m, seed, flags, bad, kept, new_counts, sc.keep);
+  c->launches++;
 }
-static void launch_write(cco_ctx *c, const DevRaw &raw, const HeavyRows &h, const SampleScratch &sc, const uint32_t *new_ptr,
-                         const uint32_t *out_base, int32_t *new_col) {
-  if (raw.n_rows <= 0) return;
-  const long long q_lo = raw.q_base, q_hi = raw.q_base + raw.nnz;
-  k_downsample_write<kSG><<<grid_for(raw.n_rows * kSG, 256, c->sm_count), 256, 0, c->stream>>>(raw.n_rows, raw.row_base, raw.rp, raw.col, q_lo, q_hi,
-                                                                                             sc.keep, nullptr, nullptr, new_ptr, out_base, new_col);
-  k_downsample_write<32><<<c->sm_count * 4, 256, 0, c->stream>>>(raw.n_rows, raw.row_base, raw.rp, raw.col, q_lo, q_hi, sc.keep, h.list, h.n,
-                                                                 new_ptr, out_base, new_col);
-  c->launches += 2;
+// pass 2: order-preserving compaction of the block's column indices by the keep bytes.  Kept entries keep their global
+// order, so entry ranks inside the block are offsets from the block's first kept entry: `dst` is where that one goes.
+static int launch_write(cco_ctx *c, Arena &ar, const DevRaw &raw, const SampleScratch &sc, int32_t *dst) {
+  if (raw.n_rows <= 0 || raw.nnz <= 0) return CCO_OK;
+  long long *n_sel;
+  CKR(ar.alloc(&n_sel, 1));
+  size_t tb = 0;
+  CK(cub::DeviceSelect::Flagged(nullptr, tb, raw.col + raw.q_base, sc.keep, dst, n_sel, (long long)raw.nnz, c->stream));
+  void *tmp;
+  CKR(ar.alloc((char **)&tmp, tb));
+  CK(cub::DeviceSelect::Flagged(tmp, tb, raw.col + raw.q_base, sc.keep, dst, n_sel, (long long)raw.nnz, c->stream));
+  ar.release(tmp);
+  c->launches += 2;   // init + select kernel
+  return CCO_OK;
 }
 
 // sampleDownAndBinarize of one whole matrix on this GPU (raw column counts already final in raw_counts)
-static int downsample_device(cco_ctx *c, Arena &ar, const DevRaw &raw, const HeavyRows &heavy, const int32_t *raw_counts, int32_t m,
+static int downsample_device(cco_ctx *c, Arena &ar, const DevRaw &raw, const int *bad, const int32_t *raw_counts, int32_t m,
                              int32_t seed, uint32_t flags, DevMat *out) {
   out->n_rows = raw.n_rows;
   out->n_cols = raw.n_cols;
@@ -526,12 +532,12 @@ static int downsample_device(cco_ctx *c, Arena &ar, const DevRaw &raw, const Hea
   if (!out->marg) CKR(ar.alloc(&out->marg, std::max<int32_t>(raw.n_cols, 1)));
   CKR(ar.alloc(&out->col, std::max<long long>(raw.nnz, 1)));
   CK(cudaMemsetAsync(out->marg, 0, sizeof(int32_t) * std::max<int32_t>(raw.n_cols, 1), c->stream));
-  CK(cudaMemsetAsync(kept + raw.n_rows, 0, 4, c->stream));
+  CK(cudaMemsetAsync(kept, 0, sizeof(uint32_t) * ((size_t)raw.n_rows + 1), c->stream));
   SampleScratch sc;
   CKR(sample_scratch(c, ar, raw, raw_counts, m, &sc));
-  launch_count(c, raw, heavy, sc, m, seed, flags, kept, out->marg);
+  launch_count(c, raw, sc, m, seed, flags, bad, kept, out->marg);
   CKR(exclusive_sum_u32(c, ar, kept, out->rp, raw.n_rows + 1));
-  launch_write(c, raw, heavy, sc, out->rp, nullptr, out->col);
+  CKR(launch_write(c, ar, raw, sc, out->col));
   CK(cudaGetLastError());
   ar.release(kept);
   ar.release(sc.col_thr);
@@ -551,7 +557,7 @@ static int nccl_check(int rc, const char *what) {
 //   (3) all-reduce of the post-sample column counts             -> marginals (nothing is re-counted on the gathered matrix)
 //   (4) all-gather of the sampled column blocks, each padded to the largest sampled block (the block sizes come from the
 //       scanned row_ptr through one mailbox record: an event wait, not a stream sync), then a pack kernel.
-static int downsample_sharded_all(cco_ctx *c, Arena &ar, const std::vector<DevRaw> &raw, const std::vector<HeavyRows> &heavy,
+static int downsample_sharded_all(cco_ctx *c, Arena &ar, const std::vector<DevRaw> &raw, const int *d_check /* [2 * n_mats] */,
                                   const std::vector<long long> &block_cap,
                                   long long U, const int32_t *raw_counts, int32_t *marg_all, const std::vector<long long> &col_off,
                                   const cco_indicator_params_t *params, int32_t seed, uint32_t flags, std::vector<DevMat> &dm,
@@ -571,7 +577,7 @@ static int downsample_sharded_all(cco_ctx *c, Arena &ar, const std::vector<DevRa
     CKR(ar.alloc(&out->rp, U + 1));
     CK(cudaMemsetAsync(kept[i], 0, sizeof(uint32_t) * (size_t)(W * S + 1), s));
     CKR(sample_scratch(c, ar, raw[i], raw_counts + col_off[i], params[i].max_interactions, &sc[i]));
-    launch_count(c, raw[i], heavy[i], sc[i], params[i].max_interactions, seed, flags, kept[i], out->marg);
+    launch_count(c, raw[i], sc[i], params[i].max_interactions, seed, flags, d_check + 2 * i, kept[i], out->marg);
   }
   CK(cudaEventRecord(stage_ev[0], s));
   if (S > 0) {
@@ -604,7 +610,7 @@ static int downsample_sharded_all(cco_ctx *c, Arena &ar, const std::vector<DevRa
     if (cap[i] == 0) continue;
     CKR(ar.alloc(&gathered[i], (size_t)(cap[i] * W)));
     // this rank's block goes straight into its slot of the gather buffer, relative to the block's first entry
-    launch_write(c, raw[i], heavy[i], sc[i], dm[i].rp, dm[i].rp + row_base, gathered[i] + (size_t)r * cap[i]);
+    CKR(launch_write(c, ar, raw[i], sc[i], gathered[i] + (size_t)r * cap[i]));
     ar.release(sc[i].col_thr);
     ar.release(sc[i].keep);
   }
@@ -1289,11 +1295,11 @@ static int train_dataset(cco_ctx *c, const cco_dataset *ds, const cco_indicator_
   // sampleDownAndBinarize every matrix
   std::vector<DevMat> dm(n_mats);
   if (c->world > 1) {
-    CKR(downsample_sharded_all(c, ar, raw, heavy, ds->block_cap, n_users, raw_counts, marg_all, col_off, params, seed, flags, dm, &sev[2]));
+    CKR(downsample_sharded_all(c, ar, raw, d_check, ds->block_cap, n_users, raw_counts, marg_all, col_off, params, seed, flags, dm, &sev[2]));
   } else {
     for (int i = 0; i < n_mats; ++i) {
       dm[i].marg = marg_all + col_off[i];
-      CKR(downsample_device(c, ar, raw[i], heavy[i], raw_counts + col_off[i], params[i].max_interactions, seed, flags, &dm[i]));
+      CKR(downsample_device(c, ar, raw[i], d_check + 2 * i, raw_counts + col_off[i], params[i].max_interactions, seed, flags, &dm[i]));
     }
     CK(mark(2));   // single GPU: both passes are booked on stage 2 ... 4 as one block
     CK(mark(3));
@@ -2350,9 +2356,7 @@ int cco_debug_downsample(cco_ctx_t *c, const cco_csr_t *m, int32_t max_interacti
   if (raw.nnz > 0 && m->n_rows > 0)
     k_col_histogram<<<grid_for(raw.nnz, 256, c->sm_count), 256, 0, c->stream>>>(0, m->n_rows, raw.rp, raw.col, raw.n_cols, counts, 1, 0);
   DevMat dm;
-  HeavyRows hv;
-  CKR(list_heavy_rows(c, ar, raw, &hv));
-  CKR(downsample_device(c, ar, raw, hv, counts, max_interactions, seed, flags, &dm));
+  CKR(downsample_device(c, ar, raw, nullptr, counts, max_interactions, seed, flags, &dm));
   std::vector<uint32_t> rp32((size_t)m->n_rows + 1);
   CK(cudaMemcpyAsync(rp32.data(), dm.rp, sizeof(uint32_t) * rp32.size(), cudaMemcpyDeviceToHost, c->stream));
   if (raw_col_counts && m->n_cols > 0)
@@ -2403,9 +2407,7 @@ int cco_debug_cooccurrence(cco_ctx_t *c, const cco_csr_t *a, const cco_csr_t *b,
     CK(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)std::max<int32_t>(raw[i].n_cols, 1), s));
     if (raw[i].nnz > 0 && raw[i].n_rows > 0)
       k_col_histogram<<<grid_for(raw[i].nnz, 256, c->sm_count), 256, 0, s>>>(0, raw[i].n_rows, raw[i].rp, raw[i].col, raw[i].n_cols, counts, 1, 0);
-    HeavyRows hv;
-    CKR(list_heavy_rows(c, ar, raw[i], &hv));
-    CKR(downsample_device(c, ar, raw[i], hv, counts, 0x7fffffff, 0, 0, &dm[i]));
+    CKR(downsample_device(c, ar, raw[i], nullptr, counts, 0x7fffffff, 0, 0, &dm[i]));
   }
   const int32_t n_items_a = dm[0].n_cols;
   uint32_t *at_ptr, *cursor, *marg_pad;
