@@ -1267,19 +1267,23 @@ static int train_dataset(cco_ctx *c, const cco_dataset *ds, const cco_indicator_
   CK(cudaMemsetAsync(raw_counts, 0, sizeof(int32_t) * (size_t)copy_stride * kHistCopies, s));
   CK(cudaMemsetAsync(marg_all, 0, sizeof(int32_t) * (size_t)copy_stride, s));
   CK(cudaMemsetAsync(d_check, 0, sizeof(int) * 2 * n_mats, s));
-  std::vector<HeavyRows> heavy(n_mats);
   for (int i = 0; i < n_mats; ++i) {
     CK(cudaStreamWaitEvent(s, ds->ready[i], 0));  // matrix i has landed (async upload: later ones may still be in flight)
     if (ds->n_local == 0) continue;
-    CKR(list_heavy_rows(c, ar, raw[i], &heavy[i]));
-    if (!ds->validated) {
-      // CCO_FLAG_ASSUME_CANONICAL skips the canonicalisation, not the safety net: a malformed matrix still fails the call
-      // (until the verdict is read the passes below skip whatever points outside the block or the column space)
-      launch_check(c, raw[i], heavy[i], d_check + 2 * i);
+    // CCO_FLAG_ASSUME_CANONICAL skips the canonicalisation, not the safety net: a malformed matrix still fails the call
+    // (until the verdict is read, the histogram skips ids outside the column space and the sampler keeps nothing)
+    int *verdict = ds->validated ? nullptr : d_check + 2 * i;
+    if (verdict) {
+      k_check_row_ptr<<<grid_for(raw[i].n_rows, 256, c->sm_count), 256, 0, s>>>(raw[i].n_rows, raw[i].rp, raw[i].q_base, raw[i].q_base + raw[i].nnz,
+                                                                              verdict);
+      c->launches++;
     }
-    k_col_histogram<<<grid_for(raw[i].nnz + 1, 256, c->sm_count), 256, 0, s>>>(0, ds->n_local, raw[i].rp, raw[i].col, raw[i].n_cols,
-                                                                                       raw_counts + col_off[i], kHistCopies, copy_stride);
-    c->launches++;
+    if (raw[i].nnz > 0) {
+      // warp-aggregated (__match_any_sync) before the atomics: 0.50 ms for the four C3 matrices against 0.53 ms without
+      k_col_histogram_flat<true><<<grid_for(raw[i].nnz, 256, c->sm_count), 256, 0, s>>>(raw[i].nnz, raw[i].col + raw[i].q_base, raw[i].n_cols,
+                                                                                       raw_counts + col_off[i], kHistCopies, copy_stride, verdict);
+      c->launches++;
+    }
   }
   if (total_cols > 0) {
     k_sum_copies<<<grid_for(total_cols, 256, c->sm_count), 256, 0, s>>>(total_cols, kHistCopies, copy_stride, raw_counts);

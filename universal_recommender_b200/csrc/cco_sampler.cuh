@@ -157,4 +157,44 @@ __global__ void __launch_bounds__(256) k_sample_count(long long n_rows, long lon
   }
 }
 
+// ---- validation + raw column counts of a not yet validated block, entry-parallel ------------------------------------------
+// The in-train safety net needs only "malformed or not" (canonical order is the caller's promise under
+// CCO_FLAG_ASSUME_CANONICAL, and the synchronous upload canonicalises): row_ptr is checked per row, column ids are checked
+// by the pass that reads every column id anyway -- the raw column histogram (numNonZeroElementsPerColumn).
+__global__ void k_check_row_ptr(long long n_rows, const long long *__restrict__ rp, long long q_lo, long long q_hi, int *flags) {
+  int bad = 0;
+  for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n_rows; r += (long long)gridDim.x * blockDim.x) {
+    const long long s = rp[r], e = rp[r + 1];
+    if (e < s || s < q_lo || e > q_hi) bad = 1;
+  }
+  if (bad) atomicOr(&flags[0], 1);
+}
+// counts[j] += 1 for every stored entry of the block (col = the block's first entry, n entries); ids outside [0, n_cols)
+// are skipped and, with `flags`, reported.  Replicated counters as in k_col_histogram.  AGG: aggregate equal ids of a warp
+// first (__match_any_sync).
+template <bool AGG>
+__global__ void k_col_histogram_flat(long long n, const int32_t *__restrict__ col, int32_t n_cols, int32_t *__restrict__ counts, int n_copies,
+                                     long long copy_stride, int *flags /* nullable */) {
+  int32_t *mine = counts + (long long)(blockIdx.x % n_copies) * copy_stride;
+  const int lane = threadIdx.x & 31;
+  int bad = 0;
+  for (long long q0 = blockIdx.x * (long long)blockDim.x + (threadIdx.x & ~31); q0 < n; q0 += (long long)gridDim.x * blockDim.x) {
+    const long long q = q0 + lane;
+    const bool act = q < n;
+    const int32_t j = act ? col[q] : -1;
+    const bool ok = act && (uint32_t)j < (uint32_t)n_cols;
+    if (act && !ok) bad = 1;
+    if (AGG) {
+      const unsigned om = __ballot_sync(0xffffffffu, ok);
+      if (ok) {
+        const unsigned peers = __match_any_sync(om, j);
+        if ((__ffs(peers) - 1) == lane) atomicAdd(&mine[j], __popc(peers));
+      }
+    } else if (ok) {
+      atomicAdd(&mine[j], 1);
+    }
+  }
+  if (flags && bad) atomicOr(&flags[0], 1);
+}
+
 }  // namespace cco
