@@ -276,8 +276,8 @@ class ShmModel:
 
 
 def source_build_id() -> str:
-    """hash of the kernel source (cco_kernels.cuh holds k_rows and every preparation kernel): a committed ncu traffic
-    figure is only quoted for the kernels it was measured on"""
+    """hash of the source file that holds k_rows (cco_kernels.cuh): the committed ncu DRAM-traffic figure of k_rows is
+    only quoted for the row kernel it was measured on (the entry-parallel preparation kernels live in cco_sampler.cuh)"""
     import hashlib
     h = hashlib.sha1()
     for f in ("cco_kernels.cuh",):
