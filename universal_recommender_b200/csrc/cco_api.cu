@@ -495,7 +495,7 @@ static int sample_scratch(cco_ctx *c, Arena &ar, const DevRaw &raw, const int32_
   return CCO_OK;
 }
 // pass 1 (k_sample_count, cco_sampler.cuh): entry-parallel; `kept` must be zero for the block's rows; `bad` (nullable) is the
-// device verdict of k_check_rows -- a malformed matrix keeps nothing, so pass 2 can never write more than row_ptr promises
+// device verdict of k_check_row_ptr / k_col_histogram_flat -- a malformed matrix keeps nothing, so pass 2 can never write more than row_ptr promises
 static void launch_count(cco_ctx *c, const DevRaw &raw, const SampleScratch &sc, int32_t m, int32_t seed, uint32_t flags, const int *bad,
                          uint32_t *kept, int32_t *new_counts) {
   if (raw.n_rows <= 0 || raw.nnz <= 0) return;

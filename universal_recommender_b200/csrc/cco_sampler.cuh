@@ -17,7 +17,7 @@
 //   * the owner lane counts the kept entries of its row from the ballot and a lane-range mask -- no shuffles, no atomics
 //     inside the chunk; one atomicAdd per (row, window) when the window slides or the chunk ends (rows may straddle chunks).
 // Every lane does useful work on every entry, rows of any length are split evenly over warps, and the kernel only
-// dereferences entry offsets inside [q_lo, q_hi): a malformed row_ptr (reported by k_check_rows) cannot send it out of bounds.
+// dereferences entry offsets inside [q_lo, q_hi): a malformed row_ptr (reported by k_check_row_ptr) cannot send it out of bounds.
 // Pass 2 is an order-preserving stream compaction by the keep bytes (cub::DeviceSelect::Flagged in cco_api.cu): kept
 // entries keep their global order, so their rank inside the block is their offset from the block's first kept entry.
 //
@@ -52,7 +52,7 @@ __device__ __forceinline__ long long warp_find_row(const long long *__restrict__
 __global__ void __launch_bounds__(256) k_sample_count(long long n_rows, long long row_base, const long long *__restrict__ rp,
                                                       const int32_t *__restrict__ col, int32_t n_cols, long long q_lo, long long q_hi,
                                                       const unsigned long long *__restrict__ col_thr, int32_t m, int32_t seed, uint32_t flags,
-                                                      const int *__restrict__ bad /* nullable: k_check_rows' verdict */,
+                                                      const int *__restrict__ bad /* nullable: the validation verdict (k_check_row_ptr, k_col_histogram_flat) */,
                                                       uint32_t *__restrict__ kept_per_row /* zeroed */, int32_t *__restrict__ new_counts,
                                                       uint8_t *__restrict__ keep_flag) {
   const int lane = threadIdx.x & 31;
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(256) k_sample_count(long long n_rows, long lon
         const bool real_row = base + idx < n_rows;   // an entry past the last row's end (malformed row_ptr) is dropped
         bool keep = false;
         if (here) {
-          // (ids outside [0, n_cols) belong to a malformed matrix: dropped here, reported by k_check_rows)
+          // (ids outside [0, n_cols) belong to a malformed matrix: dropped here, reported by k_col_histogram_flat)
           keep = real_row && (uint32_t)j < (uint32_t)n_cols && keep_entry_thr(t_row, t_col, x_row, (uint32_t)j);
           keep_flag[q - q_lo] = keep ? 1 : 0;   // pass 2 compacts by these decisions
           if (keep && new_counts) atomicAdd(&new_counts[j], 1);
